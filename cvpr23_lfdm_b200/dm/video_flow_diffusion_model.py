@@ -1,0 +1,116 @@
+"""Host-side mirror of reference DM/modules/video_flow_diffusion_model.py `FlowDiffusion`:
+same constructor, attributes and sampling methods; the compute is the B200 engine."""
+import torch
+import torch.nn as nn
+import yaml
+from ..lfae.generator import Generator
+from ..lfae.bg_motion_predictor import BGMotionPredictor
+from ..lfae.region_predictor import RegionPredictor
+from .video_flow_diffusion import Unet3D, GaussianDiffusion
+
+
+def _cuda_if_available(m):
+    return m.cuda() if torch.cuda.is_available() else m
+
+
+class FlowDiffusion(nn.Module):
+    def __init__(self, img_size=32, num_frames=40, sampling_timesteps=250, null_cond_prob=0.1, ddim_sampling_eta=1.,
+                 timesteps=1000, dim_mults=(1, 2, 4, 8), lr=1e-4, adam_betas=(0.9, 0.99), is_train=True,
+                 only_use_flow=True, use_residual_flow=False, learn_null_cond=False, use_deconv=True,
+                 padding_mode="zeros", pretrained_pth="", config_pth=""):
+        super().__init__()
+        self.use_residual_flow, self.only_use_flow = use_residual_flow, only_use_flow
+        ckpt = torch.load(pretrained_pth, map_location="cpu") if pretrained_pth != "" else None
+        with open(config_pth) as f:
+            mp = yaml.safe_load(f)['model_params']
+
+        def frozen(mod, key):
+            if ckpt is not None:
+                mod.load_state_dict(ckpt[key])
+                mod.eval()
+                for p in mod.parameters():
+                    p.requires_grad = False
+            return mod
+
+        self.generator = frozen(_cuda_if_available(Generator(
+            num_regions=mp['num_regions'], num_channels=mp['num_channels'],
+            revert_axis_swap=mp['revert_axis_swap'], **mp['generator_params'])), 'generator')
+        self.region_predictor = frozen(_cuda_if_available(RegionPredictor(
+            num_regions=mp['num_regions'], num_channels=mp['num_channels'], estimate_affine=mp['estimate_affine'],
+            **mp['region_predictor_params'])), 'region_predictor')
+        self.bg_predictor = frozen(BGMotionPredictor(num_channels=mp['num_channels'], **mp['bg_predictor_params']),
+                                   'bg_predictor')
+        self.unet = Unet3D(dim=64, channels=3 + 256, out_grid_dim=2, out_conf_dim=1, dim_mults=dim_mults,
+                           use_bert_text_cond=True, learn_null_cond=learn_null_cond, use_final_activation=False,
+                           use_deconv=use_deconv, padding_mode=padding_mode)
+        self.diffusion = GaussianDiffusion(self.unet, image_size=img_size, num_frames=num_frames,
+                                           sampling_timesteps=sampling_timesteps, timesteps=timesteps,
+                                           loss_type='l2', use_dynamic_thres=True, null_cond_prob=null_cond_prob,
+                                           ddim_sampling_eta=ddim_sampling_eta)
+        for n in ("ref_img", "ref_img_fea", "real_vid", "real_out_vid", "real_warped_vid", "real_vid_grid",
+                  "real_vid_conf", "fake_out_vid", "fake_warped_vid", "fake_vid_grid", "fake_vid_conf",
+                  "sample_out_vid", "sample_warped_vid", "sample_vid_grid", "sample_vid_conf"):
+            setattr(self, n, None)
+        # the reference builds an Adam optimiser when is_train (:104-114); training is out of scope here,
+        # the flag is kept so that demo scripts constructing with is_train=True keep working.
+        self.is_train = is_train
+        self.lr = lr
+
+    # ---- sampling (reference :190-225) -------------------------------------------------
+    def set_sample_input(self, sample_img, sample_text):
+        self.sample_img = sample_img.cuda()
+        self.sample_text = sample_text
+
+    @torch.no_grad()
+    def sample_one_video(self, cond_scale):
+        self.sample_img_fea = self.generator.compute_fea(self.sample_img)
+        pred = self.diffusion.sample(self.sample_img_fea, cond=self.sample_text, batch_size=1, cond_scale=cond_scale)
+        if self.use_residual_flow:
+            b, _, nf, h, w = pred[:, :2].size()
+            self.sample_vid_grid = pred[:, :2] + self.get_grid(b, nf, h, w, normalize=True).to(pred.device)
+        else:
+            self.sample_vid_grid = pred[:, :2, :, :, :]
+        self.sample_vid_conf = (pred[:, 2, :, :, :].unsqueeze(dim=1) + 1) * 0.5
+        self.sample_out_vid, self.sample_warped_vid = self.generator.decode_video(
+            self.sample_img, self.sample_vid_grid, self.sample_vid_conf)
+
+    # ---- real-video branch (reference :116-143): pseudo ground-truth flow of a driving video ----------
+    def set_train_input(self, ref_img, real_vid, ref_text):
+        self.ref_img, self.real_vid, self.ref_text = ref_img.cuda(), real_vid.cuda(), ref_text
+
+    @torch.no_grad()
+    def forward(self):
+        b, _, nf, H, W = self.real_vid.size()
+        src = self.region_predictor(self.ref_img)
+        grids, confs, outs, warps = [], [], [], []
+        for idx in range(nf):
+            frame = self.real_vid[:, :, idx]
+            drv = self.region_predictor(frame)
+            bg = self.bg_predictor(self.ref_img, frame)
+            g = self.generator(self.ref_img, source_region_params=src, driving_region_params=drv, bg_params=bg)
+            grids.append(g["optical_flow"].permute(0, 3, 1, 2))
+            confs.append(g["occlusion_map"])
+            outs.append(g["prediction"])
+            warps.append(g["deformed"])
+        self.real_vid_grid, self.real_vid_conf = torch.stack(grids, 2), torch.stack(confs, 2)
+        self.real_out_vid, self.real_warped_vid = torch.stack(outs, 2), torch.stack(warps, 2)
+        self.ref_img_fea = g["bottle_neck_feat"].clone().detach()
+        if self.is_train and self.training:
+            raise NotImplementedError("diffusion training step is out of scope of the B200 inference hot path")
+
+    def optimize_parameters(self):
+        raise NotImplementedError("training is out of scope of the B200 inference hot path (SURVEY.md §2a)")
+
+    def get_grid(self, b, nf, H, W, normalize=True):
+        if normalize:
+            hr, wr = torch.linspace(-1, 1, H), torch.linspace(-1, 1, W)
+        else:
+            hr, wr = torch.arange(0, H), torch.arange(0, W)
+        g = torch.stack(torch.meshgrid([hr, wr], indexing="ij"), -1).repeat(b, 1, 1, 1).flip(3).float()
+        return g.permute(0, 3, 1, 2).unsqueeze(dim=2).repeat(1, 1, nf, 1, 1)
+
+    def set_requires_grad(self, nets, requires_grad=False):
+        for net in (nets if isinstance(nets, list) else [nets]):
+            if net is not None:
+                for p in net.parameters():
+                    p.requires_grad = requires_grad
