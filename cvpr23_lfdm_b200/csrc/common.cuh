@@ -1,0 +1,58 @@
+// common.cuh — shared device helpers for the LFDM sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/lfdm_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+#define LFDM_CHECK_LAUNCH()                                   \
+    do {                                                      \
+        cudaError_t e__ = cudaPeekAtLastError();              \
+        if (e__ != cudaSuccess) return (int)e__;              \
+    } while (0)
+
+__host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ float join_bf16(bf16 hi, bf16 lo) { return __bfloat162float(hi) + __bfloat162float(lo); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == LFDM_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == LFDM_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return v;
+}
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + expf(-v)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// store 4 consecutive channels of one row as split-bf16 (8-byte stores into each plane)
+__device__ __forceinline__ void store_sb4(bf16* hi_plane, int64_t plane, int64_t idx, float4 v) {
+    bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+    split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+    __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+    __nv_bfloat162 c = __halves2bfloat162(l0, l1), d = __halves2bfloat162(l2, l3);
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<uint32_t*>(&a); hv.y = *reinterpret_cast<uint32_t*>(&b);
+    lv.x = *reinterpret_cast<uint32_t*>(&c); lv.y = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint2*>(hi_plane + idx) = hv;
+    *reinterpret_cast<uint2*>(hi_plane + plane + idx) = lv;
+}
+__device__ __forceinline__ void store_sb1(bf16* hi_plane, int64_t plane, int64_t idx, float v) {
+    bf16 h, l; split_bf16(v, h, l);
+    hi_plane[idx] = h; hi_plane[plane + idx] = l;
+}

@@ -1,0 +1,482 @@
+// conv_tc.cu — LFDM_ENGINE_TC: persistent, warp-specialised tcgen05 implicit-GEMM convolution for sm_100a.
+//
+//   D[128 x BN] (fp32, TMEM, double-buffered) += A[128 x 64] * B[BN x 64]^T     per (filter tap, 64-channel chunk)
+//
+// * A tiles are gathered straight from the channels-last split-bf16 activation tensor by TMA: one 5-D box
+//   {64 ch, BW, BH, BNF, plane} per tap, shifted by the tap offset; out-of-bounds coordinates are zero-filled by
+//   the TMA unit, which *is* the zero padding of the convolution.  A "virtual concat" (torch.cat of the UNet skip
+//   connections) is two tensor maps walked back to back.  Stride-2 convs read four parity views of the input.
+// * B tiles (weights, pre-split to bf16 hi/lo and packed [tap][Cout][Cin]) come from a 4-D map.
+// * fp32-class accuracy on bf16 tensor cores: x*w ~ hi*hi + hi*lo + lo*hi (3 tcgen05.mma per K step, fp32 accum).
+// * warp roles: warp0 = TMA producer, warp1 = MMA issuer (one elected thread), warp2 = TMEM allocator,
+//   warps4-7 = epilogue (tcgen05.ld -> bias/residual/activation/GroupNorm partial sums -> global stores).
+//   smem ring: full/empty mbarriers; TMEM ring: 2 accumulator stages, tmem_full/tmem_empty mbarriers.
+//
+// Replaces cuDNN/cuBLAS behind every Conv3d(1,k,k)/ConvTranspose3d/Conv2d/Linear on the path (include/lfdm_b200.h).
+#include <cuda.h>
+#include <cstring>
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;               // bf16 elements per K block = 128 bytes = one swizzle row
+constexpr int A_BYTES = BM * BK * 2; // 16 KiB per plane
+constexpr int MAX_TAPS = 52;
+
+struct TcArgs {
+    CUtensorMap tmA[8];              // [source*4 + parity view]
+    CUtensorMap tmB;
+    int32_t n_taps, tap_base;
+    int8_t tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
+    int32_t chunks[2];               // 64-channel chunks per source
+    int32_t bw, bh, bnf;             // A box (bw*bh*bnf == 128)
+    int32_t tiles_w, tiles_h, m_tiles, n_tiles;
+    int32_t ho_full, wo_full, mul, off_h, off_w;   // output row = ((nf*ho_full + h*mul+off_h)*wo_full + w*mul+off_w)
+    int32_t c_out;
+    const float* bias;
+    const float* residual;
+    int32_t res_bcast_f;
+    int64_t p_out;
+    float* out_f32;
+    int32_t f32_act;
+    bf16* out_sb;
+    int64_t out_plane;
+    int32_t sb_act;
+    const float* sb_scale;
+    const float* sb_shift;
+    double* gn_stats;
+    int32_t gn_cpg, gn_groups;
+    int64_t rows_per_sample;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    constexpr uint32_t IDESC = ptx::make_idesc_bf16(BM, BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && ptx::elect_one()) {
+        for (int i = 0; i < 8; ++i) ptx::prefetch_tensormap(&a.tmA[i]);
+        ptx::prefetch_tensormap(&a.tmB);
+    }
+    if (warp == 1 && ptx::elect_one()) {
+        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 128); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int kb_per_tap = a.chunks[0] + a.chunks[1];
+    const int n_kb = a.n_taps * kb_per_tap;
+    const int total_tiles = a.m_tiles * a.n_tiles;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (ptx::elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+                const int w_t = m_tile % a.tiles_w;
+                const int h_t = (m_tile / a.tiles_w) % a.tiles_h;
+                const int nf_t = m_tile / (a.tiles_w * a.tiles_h);
+                const int w0 = w_t * a.bw, h0 = h_t * a.bh, nf0 = nf_t * a.bnf, n0 = n_tile * BN;
+                for (int tap = 0; tap < a.n_taps; ++tap) {
+                    const int dy = a.tap_dy[tap], dx = a.tap_dx[tap], mp = a.tap_map[tap];
+                    for (int src = 0; src < 2; ++src) {
+                        const CUtensorMap* tm = &a.tmA[src * 4 + mp];
+                        const int kbase = src ? a.chunks[0] * BK : 0;
+                        for (int ch = 0; ch < a.chunks[src]; ++ch) {
+                            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                            uint8_t* s = smem + stage * STAGE_BYTES;
+                            ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                            ptx::tma_load_5d(s, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 0);
+                            ptx::tma_load_5d(s + A_BYTES, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 1);
+                            ptx::tma_load_4d(s + 2 * A_BYTES, &a.tmB, &full_bar[stage], kbase + ch * BK, n0,
+                                             a.tap_base + tap, 0);
+                            ptx::tma_load_4d(s + 2 * A_BYTES + B_BYTES, &a.tmB, &full_bar[stage], kbase + ch * BK, n0,
+                                             a.tap_base + tap, 1);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0; uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t sbase = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t da_hi = ptx::make_sw128_kmajor_desc(sbase);
+                    const uint64_t da_lo = ptx::make_sw128_kmajor_desc(sbase + A_BYTES);
+                    const uint64_t db_hi = ptx::make_sw128_kmajor_desc(sbase + 2 * A_BYTES);
+                    const uint64_t db_lo = ptx::make_sw128_kmajor_desc(sbase + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+                        const uint64_t off = (uint64_t)(ks * 2);   // 16 bf16 = 32 B, encoded >> 4
+                        ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
+                        ptx::umma_bf16(tmem_d, da_hi + off, db_lo + off, IDESC, 1u);
+                        ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC, 1u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);
+                    if (kb == n_kb - 1) ptx::umma_commit(&tfull_bar[as]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp - 4;              // == warp % 4: TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;         // tile row handled by this thread
+        const bool vec_ok = (a.c_out % 16) == 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+            const int w_t = m_tile % a.tiles_w;
+            const int h_t = (m_tile / a.tiles_w) % a.tiles_h;
+            const int nf_t = m_tile / (a.tiles_w * a.tiles_h);
+            const int n0 = n_tile * BN;
+            const int nf = nf_t * a.bnf + r / (a.bh * a.bw);
+            const int h = h_t * a.bh + (r / a.bw) % a.bh;
+            const int w = w_t * a.bw + r % a.bw;
+            const int64_t orow = ((int64_t)nf * a.ho_full + (h * a.mul + a.off_h)) * a.wo_full + (w * a.mul + a.off_w);
+            int64_t rrow = orow;
+            if (a.res_bcast_f > 0) rrow = (orow / ((int64_t)a.res_bcast_f * a.p_out)) * a.p_out + (orow % a.p_out);
+            const int bsample = a.gn_stats ? (int)(orow / a.rows_per_sample) : 0;
+
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t rr[16];
+                ptx::tmem_ld16(taddr + c0, rr);
+                ptx::tmem_ld_wait();
+                const int nb = n0 + c0;
+                if (nb >= a.c_out) continue;       // warp-uniform (padded N)
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+                const bool full = vec_ok && (nb + 16 <= a.c_out);
+                if (full) {
+                    if (a.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 b4 = *reinterpret_cast<const float4*>(a.bias + nb + j);
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    }
+                    if (a.residual) {
+                        const float* rp = a.residual + rrow * a.c_out + nb;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+                            v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+                        }
+                    }
+                    if (a.gn_stats) {
+                        // 16 columns = two 8-column halves; cpg is a multiple of 8
+                        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { s0 += v[j]; q0 = fmaf(v[j], v[j], q0); }
+#pragma unroll
+                        for (int j = 8; j < 16; ++j) { s1 += v[j]; q1 = fmaf(v[j], v[j], q1); }
+                        s0 = warp_sum(s0); q0 = warp_sum(q0); s1 = warp_sum(s1); q1 = warp_sum(q1);
+                        if (lane == 0) {
+                            const int g0 = nb / a.gn_cpg, g1 = (nb + 8) / a.gn_cpg;
+                            double* st = a.gn_stats + (int64_t)bsample * a.gn_groups * 2;
+                            if (g0 == g1) {
+                                atomicAdd(st + g0 * 2, (double)s0 + (double)s1);
+                                atomicAdd(st + g0 * 2 + 1, (double)q0 + (double)q1);
+                            } else {
+                                atomicAdd(st + g0 * 2, (double)s0); atomicAdd(st + g0 * 2 + 1, (double)q0);
+                                atomicAdd(st + g1 * 2, (double)s1); atomicAdd(st + g1 * 2 + 1, (double)q1);
+                            }
+                        }
+                    }
+                    const int64_t o = orow * a.c_out + nb;
+                    if (a.out_f32) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 o4 = make_float4(apply_act(v[j], a.f32_act), apply_act(v[j + 1], a.f32_act),
+                                                    apply_act(v[j + 2], a.f32_act), apply_act(v[j + 3], a.f32_act));
+                            *reinterpret_cast<float4*>(a.out_f32 + o + j) = o4;
+                        }
+                    }
+                    if (a.out_sb) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float u[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float t = v[j + e];
+                                if (a.sb_scale) t *= a.sb_scale[nb + j + e];
+                                if (a.sb_shift) t += a.sb_shift[nb + j + e];
+                                u[e] = apply_act(t, a.sb_act);
+                            }
+                            store_sb4(a.out_sb, a.out_plane, o + j, make_float4(u[0], u[1], u[2], u[3]));
+                        }
+                    }
+                } else {
+                    // ragged N (e.g. Cout = 3): scalar, masked
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = nb + j;
+                        if (n < a.c_out) {
+                            float t = v[j];
+                            if (a.bias) t += a.bias[n];
+                            if (a.residual) t += a.residual[rrow * a.c_out + n];
+                            const int64_t o = orow * a.c_out + n;
+                            if (a.out_f32) a.out_f32[o] = apply_act(t, a.f32_act);
+                            if (a.out_sb) {
+                                float u = t;
+                                if (a.sb_scale) u *= a.sb_scale[n];
+                                if (a.sb_shift) u += a.sb_shift[n];
+                                store_sb1(a.out_sb, a.out_plane, o, apply_act(u, a.sb_act));
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return LFDM_E_NODRIVER;
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                     strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (1000 + (int)r);
+}
+
+template <int BN, int STAGES>
+int launch(const TcArgs& a, cudaStream_t st) {
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BN * BK * 2;
+    constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    int total = a.m_tiles * a.n_tiles;
+    int grid = total < num_sms ? total : num_sms;
+    conv_tc_kernel<BN, STAGES><<<grid, 256, SMEM, st>>>(a);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
+    if (!d || !d->w_sb) return LFDM_E_BADARG;
+    // ---- operand checks
+    int nsrc = d->a_c[1] > 0 ? 2 : 1;
+    for (int s = 0; s < nsrc; ++s) {
+        if (!d->a_sb[s] || (d->a_c[s] % BK) != 0) return LFDM_E_UNSUPP;
+        if (reinterpret_cast<uintptr_t>(d->a_sb[s]) & 15) return LFDM_E_UNSUPP;
+    }
+    if (d->reflect) return LFDM_E_UNSUPP;
+    const int cin_total = d->a_c[0] + d->a_c[1];
+
+    // ---- iteration geometry (the grid the M tiles walk) and per-launch tap lists
+    int ht, wt, mul = 1, n_launch = 1, taps_per_launch, total_taps;
+    bool parity_views = false;
+    if (d->mode == LFDM_CONV_DIRECT && d->stride == 1) {
+        if (d->h_out != d->h_in || d->w_out != d->w_in || d->kh * d->kw > MAX_TAPS) return LFDM_E_UNSUPP;
+        ht = d->h_out; wt = d->w_out; taps_per_launch = d->kh * d->kw; total_taps = taps_per_launch;
+    } else if (d->mode == LFDM_CONV_DIRECT && d->stride == 2) {
+        if (d->kh != 4 || d->kw != 4 || d->pad != 1 || d->h_out * 2 != d->h_in || d->w_out * 2 != d->w_in) return LFDM_E_UNSUPP;
+        ht = d->h_out; wt = d->w_out; taps_per_launch = 16; total_taps = 16; parity_views = true;
+    } else if (d->mode == LFDM_CONV_TRANSPOSED) {
+        if (d->kh != 4 || d->kw != 4 || d->pad != 1 || d->stride != 2 || d->h_out != 2 * d->h_in || d->w_out != 2 * d->w_in) return LFDM_E_UNSUPP;
+        ht = d->h_in; wt = d->w_in; mul = 2; n_launch = 4; taps_per_launch = 4; total_taps = 16;
+    } else if (d->mode == LFDM_CONV_UPNEAREST) {
+        if (d->kh != 3 || d->kw != 3 || d->pad != 1 || d->h_out != 2 * d->h_in || d->w_out != 2 * d->w_in) return LFDM_E_UNSUPP;
+        ht = d->h_in; wt = d->w_in; mul = 2; n_launch = 4; taps_per_launch = 4; total_taps = 16;
+    } else {
+        return LFDM_E_UNSUPP;
+    }
+    int bw = wt < 128 ? wt : 128;
+    if (wt % bw) return LFDM_E_UNSUPP;
+    int bh = ht < 128 / bw ? ht : 128 / bw;
+    if (bh < 1 || ht % bh) return LFDM_E_UNSUPP;
+    if (128 % (bw * bh)) return LFDM_E_UNSUPP;
+    int bnf = 128 / (bw * bh);
+    if (d->nf % bnf) return LFDM_E_UNSUPP;
+    if (bw > 256 || bh > 256 || bnf > 256) return LFDM_E_UNSUPP;
+
+    // ---- N tile
+    int bn;
+    if (d->c_out % 128 == 0) bn = 128;
+    else if (d->c_out % 64 == 0) bn = 64;
+    else if (d->c_out % 32 == 0) bn = 32;
+    else if (d->c_out <= 16) bn = 16;
+    else return LFDM_E_UNSUPP;
+    const int c_out_pad = ((d->c_out + bn - 1) / bn) * bn;
+    if (d->gn_stats && ((d->gn_cpg % 8) != 0 || d->rows_per_sample % 128 != 0 || mul != 1)) return LFDM_E_UNSUPP;
+
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    // ---- tensor maps: activations
+    for (int s = 0; s < 2; ++s) {
+        int src = s < nsrc ? s : 0;   // unused maps alias source 0 (never dereferenced: chunks == 0)
+        const bf16* base = reinterpret_cast<const bf16*>(d->a_sb[src]);
+        const cuuint64_t C = (cuuint64_t)d->a_c[src], W = (cuuint64_t)d->w_in, H = (cuuint64_t)d->h_in;
+        for (int v = 0; v < 4; ++v) {
+            int rc;
+            if (parity_views) {
+                const int ph = v >> 1, pw = v & 1;
+                cuuint64_t dims[5] = {C, W / 2, H / 2, (cuuint64_t)d->nf, 2};
+                cuuint64_t strides[4] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2, (cuuint64_t)d->a_plane[src] * 2};
+                cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bnf, 1};
+                rc = make_map(&a.tmA[s * 4 + v], base + ((int64_t)ph * W + pw) * C, 5, dims, strides, box);
+            } else {
+                cuuint64_t dims[5] = {C, W, H, (cuuint64_t)d->nf, 2};
+                cuuint64_t strides[4] = {C * 2, W * C * 2, H * W * C * 2, (cuuint64_t)d->a_plane[src] * 2};
+                cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bnf, 1};
+                rc = make_map(&a.tmA[s * 4 + v], base, 5, dims, strides, box);
+            }
+            if (rc) return rc;
+        }
+    }
+    // ---- weights: [plane][tap][c_out_pad][cin_total]
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)cin_total, (cuuint64_t)c_out_pad, (cuuint64_t)total_taps, 2};
+        cuuint64_t strides[3] = {(cuuint64_t)cin_total * 2, (cuuint64_t)cin_total * c_out_pad * 2, (cuuint64_t)d->w_plane * 2};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bn, 1, 1};
+        int rc = make_map(&a.tmB, d->w_sb, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    a.chunks[0] = d->a_c[0] / BK;
+    a.chunks[1] = nsrc > 1 ? d->a_c[1] / BK : 0;
+    a.bw = bw; a.bh = bh; a.bnf = bnf;
+    a.tiles_w = wt / bw; a.tiles_h = ht / bh;
+    a.m_tiles = a.tiles_w * a.tiles_h * (d->nf / bnf);
+    a.n_tiles = c_out_pad / bn;
+    a.ho_full = d->h_out; a.wo_full = d->w_out; a.mul = mul;
+    a.c_out = d->c_out;
+    a.bias = d->bias; a.residual = d->residual; a.res_bcast_f = d->res_bcast_f;
+    a.p_out = (int64_t)d->h_out * d->w_out;
+    a.out_f32 = d->out_f32; a.f32_act = d->f32_act;
+    a.out_sb = reinterpret_cast<bf16*>(d->out_sb); a.out_plane = d->out_plane; a.sb_act = d->sb_act;
+    a.sb_scale = d->sb_scale; a.sb_shift = d->sb_shift;
+    a.gn_stats = d->gn_stats; a.gn_cpg = d->gn_cpg > 0 ? d->gn_cpg : 8;
+    a.gn_groups = d->c_out / a.gn_cpg; a.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+    a.n_taps = taps_per_launch;
+
+    for (int L = 0; L < n_launch; ++L) {
+        a.tap_base = L * taps_per_launch;
+        a.off_h = 0; a.off_w = 0;
+        if (d->mode == LFDM_CONV_DIRECT && d->stride == 1) {
+            for (int t = 0; t < taps_per_launch; ++t) {
+                a.tap_map[t] = 0; a.tap_dy[t] = (int8_t)(t / d->kw - d->pad); a.tap_dx[t] = (int8_t)(t % d->kw - d->pad);
+            }
+        } else if (parity_views) {
+            // input row = 2*ho - 1 + kh = 2*(ho + a) + ph  with (kh - 1) = 2a + ph
+            for (int t = 0; t < 16; ++t) {
+                int kh = t / 4, kw = t % 4;
+                int eh = kh - 1, ew = kw - 1;
+                int ph = eh & 1, pw = ew & 1;              // two's complement: (-1 & 1) == 1
+                int ah = (eh - ph) / 2, aw = (ew - pw) / 2;
+                a.tap_map[t] = (int8_t)(ph * 2 + pw); a.tap_dy[t] = (int8_t)ah; a.tap_dx[t] = (int8_t)aw;
+            }
+        } else {
+            // 2x2 sub-kernels per output parity (p, q); weights packed [phase][tap = a*2+b] by the host packer
+            const int p = L >> 1, qq = L & 1;
+            a.off_h = p; a.off_w = qq;
+            int dyl[2], dxl[2];
+            if (d->mode == LFDM_CONV_TRANSPOSED) {          // p=0: kh in {1,3} -> dy {0,-1};  p=1: kh in {0,2} -> dy {+1,0}
+                dyl[0] = p ? 1 : 0; dyl[1] = p ? 0 : -1;
+                dxl[0] = qq ? 1 : 0; dxl[1] = qq ? 0 : -1;
+            } else {                                        // up-nearest: p=0: dy {-1,0};  p=1: dy {0,+1}
+                dyl[0] = p ? 0 : -1; dyl[1] = p ? 1 : 0;
+                dxl[0] = qq ? 0 : -1; dxl[1] = qq ? 1 : 0;
+            }
+            for (int t = 0; t < 4; ++t) { a.tap_map[t] = 0; a.tap_dy[t] = (int8_t)dyl[t >> 1]; a.tap_dx[t] = (int8_t)dxl[t & 1]; }
+        }
+        int rc;
+        switch (bn) {
+            case 128: rc = launch<128, 3>(a, st); break;
+            case 64: rc = launch<64, 4>(a, st); break;
+            case 32: rc = launch<32, 4>(a, st); break;
+            default: rc = launch<16, 4>(a, st); break;
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}

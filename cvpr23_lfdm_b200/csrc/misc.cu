@@ -1,0 +1,280 @@
+// misc.cu — embedding MLPs, layout conversion and small element-wise kernels of the LFDM hot path.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float act_f(float v, int act) {
+    if (act == 1) return silu_f(v);
+    if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));   // nn.GELU() (erf form)
+    return v;
+}
+
+// y[r][n] = act_out(sum_k act_in(x[r][k]) W[n][k] + b[n]); one warp per output column n, W row cached in registers.
+// time_mlp (video_flow_diffusion.py:422-428) and the per-block (scale,shift) MLPs (:217-220,230-232).
+template <int KPL>   // k values per lane (k <= 32*KPL)
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ b, float* __restrict__ y, int rows,
+                                                           int k, int n, int act_in, int act_out) {
+    const int lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (col >= n) return;
+    float wr[KPL];
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+        int kk = lane + 32 * j;
+        wr[j] = kk < k ? w[(int64_t)col * k + kk] : 0.f;
+    }
+    const float bias = b ? b[col] : 0.f;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            int kk = lane + 32 * j;
+            if (kk < k) acc = fmaf(act_f(x[(int64_t)r * k + kk], act_in), wr[j], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) y[(int64_t)r * n + col] = act_f(acc + bias, act_out);
+    }
+}
+
+__global__ void sinusoidal_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
+                                  float* __restrict__ out, int rows, int dim) {
+    const int half = dim / 2;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * half) return;
+    int r = i / half, j = i % half;
+    float a = (float)t[r] * freqs[j];
+    out[r * dim + j] = sinf(a);
+    out[r * dim + half + j] = cosf(a);
+}
+
+__global__ void ss_combine_kernel(const float* __restrict__ time_tab, const int32_t* __restrict__ step_idx,
+                                  const float* __restrict__ cond_tab, float* __restrict__ ss, int b, int n) {
+    const int row = step_idx ? *step_idx : 0;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b * n) return;
+    int j = i % n;
+    ss[i] = time_tab[(int64_t)row * n + j] + cond_tab[i];
+}
+
+// in[b][c][f][p] -> rows[(b*F+f)*P + p][c_pad]; 32x32 smem transpose tile; grid (P/32, c_pad/32, B*F)
+__global__ void __launch_bounds__(256) to_rows_kernel(const float* __restrict__ in, int c, int f, int p, int64_t sb,
+                                                      int64_t sc, int64_t sf, int c_pad, bf16* __restrict__ out_sb,
+                                                      int64_t out_plane, float* __restrict__ out_f32) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, bi = n / f, fi = n % f;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int cc = c0 + ty + 8 * j, pp = p0 + tx;
+        float v = 0.f;
+        if (cc < c && pp < p) v = in[bi * sb + cc * sc + fi * sf + pp];
+        tile[ty + 8 * j][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int pp = p0 + ty + 8 * j, cc = c0 + tx;
+        if (pp < p && cc < c_pad) {
+            float v = tile[tx][ty + 8 * j];
+            int64_t o = ((int64_t)n * p + pp) * c_pad + cc;
+            if (out_f32) out_f32[o] = v;
+            if (out_sb) store_sb1(out_sb, out_plane, o, v);
+        }
+    }
+}
+
+// rows[(b*F+f)*P+p][ld] -> out[b][c][f][p]
+__global__ void __launch_bounds__(256) from_rows_kernel(const float* __restrict__ rows, int ld, int c, int f, int p,
+                                                        float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, bi = n / f, fi = n % f;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int pp = p0 + ty + 8 * j, cc = c0 + tx;
+        float v = 0.f;
+        if (pp < p && cc < c) v = rows[((int64_t)n * p + pp) * ld + cc];
+        tile[ty + 8 * j][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int cc = c0 + ty + 8 * j, pp = p0 + tx;
+        if (cc < c && pp < p) out[(((int64_t)bi * c + cc) * f + fi) * p + pp] = tile[tx][ty + 8 * j];
+    }
+}
+
+// in[b][c][f][h][w] -> SB rows [M][k_pad], k = (kh*ks + kw)*c + ch, zero padded borders / k >= ks*ks*c
+__global__ void __launch_bounds__(256) im2col_small_kernel(const float* __restrict__ in, int c, int f, int h, int w,
+                                                           int ks, int pad, int k_pad, bf16* __restrict__ out_sb,
+                                                           int64_t out_plane, int64_t total) {
+    const int kreal = ks * ks * c;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int k = (int)(i % k_pad);
+        int64_t m = i / k_pad;
+        float v = 0.f;
+        if (k < kreal) {
+            int tap = k / c, ch = k - tap * c;
+            int kh = tap / ks, kw = tap - kh * ks;
+            int x = (int)(m % w);
+            int y = (int)((m / w) % h);
+            int64_t n = m / ((int64_t)h * w);
+            int bi = (int)(n / f), fi = (int)(n % f);
+            int yy = y - pad + kh, xx = x - pad + kw;
+            if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+                v = in[((((int64_t)bi * c + ch) * f + fi) * h + yy) * w + xx];
+        }
+        store_sb1(out_sb, out_plane, i, v);
+    }
+}
+
+__global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__ in, int h, int w, int c,
+                                                       float* __restrict__ out_f32, bf16* __restrict__ out_sb,
+                                                       int64_t out_plane, int64_t total) {
+    const int c4 = c >> 2, ho = h >> 1, wo = w >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cq = (int)(i % c4);
+        int64_t pix = i / c4;
+        int x = (int)(pix % wo);
+        int y = (int)((pix / wo) % ho);
+        int64_t n = pix / ((int64_t)ho * wo);
+        const float* b = in + (((int64_t)n * h + 2 * y) * w + 2 * x) * c + cq * 4;
+        float4 a0 = *reinterpret_cast<const float4*>(b), a1 = *reinterpret_cast<const float4*>(b + c);
+        float4 a2 = *reinterpret_cast<const float4*>(b + (int64_t)w * c), a3 = *reinterpret_cast<const float4*>(b + (int64_t)w * c + c);
+        float4 r = make_float4((a0.x + a1.x + a2.x + a3.x) * 0.25f, (a0.y + a1.y + a2.y + a3.y) * 0.25f,
+                               (a0.z + a1.z + a2.z + a3.z) * 0.25f, (a0.w + a1.w + a2.w + a3.w) * 0.25f);
+        int64_t o = pix * c + cq * 4;
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = r;
+        if (out_sb) store_sb4(out_sb, out_plane, o, r);
+    }
+}
+
+// one warp per row: out[b][ch][f][p] = dot(a[m], wa[ch]) + ba[ch]  (ch < na)  |  dot(o[m], wo[ch-na]) + bo
+__global__ void __launch_bounds__(256) unet_heads_kernel(const float* __restrict__ a, const float* __restrict__ wa,
+                                                         const float* __restrict__ ba, int na,
+                                                         const float* __restrict__ o, const float* __restrict__ wo,
+                                                         const float* __restrict__ bo, int no, int c, int f, int p,
+                                                         int64_t m_total, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nch = na + no;
+    for (int64_t m = warp; m < m_total; m += nwarps) {
+        const int64_t n = m / p;
+        const int pp = (int)(m % p);
+        const int bi = (int)(n / f), fi = (int)(n % f);
+        for (int ch = 0; ch < nch; ++ch) {
+            const float* src = ch < na ? a : o;
+            const float* wv = ch < na ? wa + (int64_t)ch * c : wo + (int64_t)(ch - na) * c;
+            float acc = 0.f;
+            for (int k = lane; k < c; k += 32) acc = fmaf(src[m * c + k], wv[k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                float bias = ch < na ? (ba ? ba[ch] : 0.f) : (bo ? bo[ch - na] : 0.f);
+                out[(((int64_t)bi * nch + ch) * f + fi) * p + pp] = acc + bias;
+            }
+        }
+    }
+}
+
+__global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t plane, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        store_sb1(out, plane, i, in[i]);
+}
+
+inline int grid_for(int64_t total, int cap = 148 * 32) {
+    int64_t b = (total + 255) / 256;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+extern "C" int lfdm_small_linear(const float* x, const float* w, const float* b, float* y, int rows, int k, int n,
+                                 int act_in, int act_out, void* stream) {
+    if (!x || !w || !y || rows <= 0 || k <= 0 || n <= 0 || k > 2048) return LFDM_E_BADARG;
+    dim3 grid((n + 7) / 8, rows < 64 ? rows : 64);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k <= 64) small_linear_kernel<2><<<grid, 256, 0, st>>>(x, w, b, y, rows, k, n, act_in, act_out);
+    else if (k <= 256) small_linear_kernel<8><<<grid, 256, 0, st>>>(x, w, b, y, rows, k, n, act_in, act_out);
+    else if (k <= 1024) small_linear_kernel<32><<<grid, 256, 0, st>>>(x, w, b, y, rows, k, n, act_in, act_out);
+    else small_linear_kernel<64><<<grid, 256, 0, st>>>(x, w, b, y, rows, k, n, act_in, act_out);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_sinusoidal(const int64_t* t, const float* freqs, float* out, int rows, int dim, void* stream) {
+    if (!t || !freqs || !out || dim < 2 || (dim & 1)) return LFDM_E_BADARG;
+    int total = rows * (dim / 2);
+    sinusoidal_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, freqs, out, rows, dim);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_ss_combine(const float* time_tab, const int32_t* step_idx, const float* cond_tab, float* ss, int b,
+                               int n, void* stream) {
+    if (!time_tab || !cond_tab || !ss) return LFDM_E_BADARG;
+    int total = b * n;
+    ss_combine_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(time_tab, step_idx, cond_tab, ss, b, n);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_to_rows(const float* in, int b, int c, int f, int p, int64_t sb, int64_t sc, int64_t sf, int c_pad,
+                            void* out_sb, int64_t out_plane, float* out_f32, void* stream) {
+    if (!in || c_pad < c || (!out_sb && !out_f32)) return LFDM_E_BADARG;
+    dim3 grid((p + 31) / 32, (c_pad + 31) / 32, b * f);
+    to_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, c, f, p, sb, sc, sf, c_pad, (bf16*)out_sb, out_plane, out_f32);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_from_rows(const float* rows, int ld, int b, int c, int f, int p, float* out, void* stream) {
+    if (!rows || !out || ld < c) return LFDM_E_BADARG;
+    dim3 grid((p + 31) / 32, (c + 31) / 32, b * f);
+    from_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, ld, c, f, p, out);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_im2col_small(const float* in, int b, int c, int f, int h, int w, int ksize, int pad, int k_pad,
+                                 void* out_sb, int64_t out_plane, void* stream) {
+    if (!in || !out_sb || k_pad < ksize * ksize * c) return LFDM_E_BADARG;
+    int64_t total = (int64_t)b * f * h * w * k_pad;
+    im2col_small_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, c, f, h, w, ksize, pad, k_pad,
+                                                                        (bf16*)out_sb, out_plane, total);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_avgpool2_rows(const float* in, int n, int h, int w, int c, float* out_f32, void* out_sb,
+                                  int64_t out_plane, void* stream) {
+    if (!in || (c & 3) || (h & 1) || (w & 1)) return LFDM_E_BADARG;
+    int64_t total = (int64_t)n * (h / 2) * (w / 2) * (c / 4);
+    avgpool2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, h, w, c, out_f32, (bf16*)out_sb, out_plane, total);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_unet_heads(const float* a, const float* wa, const float* ba, int na, const float* o,
+                               const float* wo, const float* bo, int no, int c, int b, int f, int p, float* out,
+                               void* stream) {
+    if (!a || !o || !wa || !wo || !out) return LFDM_E_BADARG;
+    int64_t m = (int64_t)b * f * p;
+    int64_t blocks = (m + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    unet_heads_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, wa, ba, na, o, wo, bo, no, c, f, p, m, out);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_split_bf16(const float* in, void* out_sb, int64_t out_plane, int64_t n, void* stream) {
+    if (!in || !out_sb) return LFDM_E_BADARG;
+    split_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(in, (bf16*)out_sb, out_plane, n);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,175 @@
+// norm.cu — GroupNorm statistics / apply (+scale-shift, SiLU, residual) and channel LayerNorm over row matrices.
+// HBM-bound element-wise kernels: float4 loads/stores, one pass each.
+//   GroupNorm: reference Block.forward (DM/modules/video_flow_diffusion.py:203-211) — nn.GroupNorm on a 5-D tensor:
+//              statistics span (C/groups, F, H, W) per sample; biased variance; eps inside the sqrt.
+//   LayerNorm: reference LayerNorm.forward (:176-179) — over channels, biased variance, gamma only.
+#include "common.cuh"
+
+namespace {
+
+// ---------------- GroupNorm statistics: grid (chunks, B*groups); double atomics into stats[b][g][2]
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int64_t rows_per_sample, int c,
+                                                       int cpg, int groups, double* __restrict__ stats) {
+    const int bg = blockIdx.y;
+    const int b = bg / groups, g = bg % groups;
+    const int64_t total = rows_per_sample * cpg;
+    const float* base = x + (int64_t)b * rows_per_sample * c + g * cpg;
+    float s = 0.f, ss = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / cpg;
+        int cc = (int)(i - r * cpg);
+        float v = base[r * c + cc];
+        s += v; ss = fmaf(v, v, ss);
+    }
+    __shared__ double sh[2][8];
+    s = warp_sum(s); ss = warp_sum(ss);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = (double)s; sh[1][w] = (double)ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, q = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh[0][i]; q += sh[1][i]; }
+        atomicAdd(&stats[bg * 2 + 0], a);
+        atomicAdd(&stats[bg * 2 + 1], q);
+    }
+}
+
+// ---------------- GroupNorm apply: one thread = 4 consecutive channels of one row
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ ss, const float* __restrict__ residual,
+                                                       float* __restrict__ out_f32, bf16* __restrict__ out_sb,
+                                                       int64_t out_plane, int64_t m, int c, int cpg, int groups,
+                                                       int64_t rows_per_sample, float eps, int64_t ss_stride) {
+    extern __shared__ float2 s_mr[];   // (mean, rstd) per (b, g)
+    const int c4 = c >> 2;
+    const int64_t total = m * c4;
+    const double inv_n = 1.0 / ((double)rows_per_sample * cpg);
+    const int nbg = (int)(m / rows_per_sample) * groups;
+    for (int i = threadIdx.x; i < nbg; i += blockDim.x) {
+        double mean = stats[i * 2 + 0] * inv_n;
+        double var = stats[i * 2 + 1] * inv_n - mean * mean;
+        if (var < 0) var = 0;
+        s_mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = i / c4;
+        int ch = (int)(i - row * c4) * 4;
+        int b = (int)(row / rows_per_sample);
+        float4 v = *reinterpret_cast<const float4*>(x + row * c + ch);
+        float vv[4] = {v.x, v.y, v.z, v.w};
+        float r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int cc = ch + e;
+            int g = cc / cpg;
+            float2 mr = s_mr[b * groups + g];
+            float mean = mr.x, rstd = mr.y;
+            float y = (vv[e] - mean) * rstd * gamma[cc] + beta[cc];
+            if (ss) {
+                float sc = ss[(int64_t)b * ss_stride + cc], sh = ss[(int64_t)b * ss_stride + c + cc];
+                y = y * (sc + 1.f) + sh;
+            }
+            r[e] = silu_f(y);
+        }
+        if (residual) {
+            float4 q = *reinterpret_cast<const float4*>(residual + row * c + ch);
+            r[0] += q.x; r[1] += q.y; r[2] += q.z; r[3] += q.w;
+        }
+        float4 o = make_float4(r[0], r[1], r[2], r[3]);
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * c + ch) = o;
+        if (out_sb) store_sb4(out_sb, out_plane, row * c + ch, o);
+    }
+}
+
+// ---------------- LayerNorm over channels: one warp per row; c % 4 == 0, c <= 1024
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        bf16* __restrict__ out_sb, int64_t out_plane,
+                                                        float* __restrict__ out_f32, int64_t m, int c, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int c4 = c >> 2;
+    for (int64_t row = warp; row < m; row += nwarps) {
+        float4 v[8];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int q = lane + 32 * j;
+            if (q < c4) {
+                v[j] = *reinterpret_cast<const float4*>(x + row * c + q * 4);
+                s += v[j].x + v[j].y + v[j].z + v[j].w;
+            }
+        }
+        s = warp_sum(s);
+        float mean = s / (float)c;
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int q = lane + 32 * j;
+            if (q < c4) {
+                float a = v[j].x - mean, b = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
+                sq += a * a + b * b + cc * cc + d * d;
+            }
+        }
+        sq = warp_sum(sq);
+        float rstd = 1.f / sqrtf(sq / (float)c + eps);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int q = lane + 32 * j;
+            if (q < c4) {
+                float4 g = *reinterpret_cast<const float4*>(gamma + q * 4);
+                float4 o = make_float4((v[j].x - mean) * rstd * g.x, (v[j].y - mean) * rstd * g.y,
+                                       (v[j].z - mean) * rstd * g.z, (v[j].w - mean) * rstd * g.w);
+                if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * c + q * 4) = o;
+                if (out_sb) store_sb4(out_sb, out_plane, row * c + q * 4, o);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int lfdm_gn_stats(const float* x, int64_t m, int c, int groups, int rows_per_sample, double* stats,
+                             void* stream) {
+    if (!x || !stats || groups <= 0 || c % groups || rows_per_sample <= 0 || m % rows_per_sample) return LFDM_E_BADARG;
+    int b = (int)(m / rows_per_sample);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * b * groups, st);
+    if (e != cudaSuccess) return (int)e;
+    int cpg = c / groups;
+    int64_t total = (int64_t)rows_per_sample * cpg;
+    int chunks = (int)((total + 256 * 16 - 1) / (256 * 16));
+    if (chunks < 1) chunks = 1;
+    if (chunks > 512) chunks = 512;
+    gn_stats_kernel<<<dim3(chunks, b * groups), 256, 0, st>>>(x, rows_per_sample, c, cpg, groups, stats);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_gn_apply(const float* x, const double* stats, const float* gamma, const float* beta,
+                             const float* ss, int64_t ss_stride, const float* residual, float* out_f32, void* out_sb, int64_t out_plane,
+                             int64_t m, int c, int groups, int rows_per_sample, float eps, void* stream) {
+    if (!x || !stats || !gamma || !beta || (c & 3) || c % groups || m % rows_per_sample) return LFDM_E_BADARG;
+    int64_t total = m * (c >> 2);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    size_t smem = sizeof(float2) * (size_t)(m / rows_per_sample) * groups;
+    if (smem > 40000) return LFDM_E_UNSUPP;
+    gn_apply_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(x, stats, gamma, beta, ss, residual, out_f32,
+                                                             (bf16*)out_sb, out_plane, m, c, c / groups, groups,
+                                                             rows_per_sample, eps, ss_stride);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_layernorm(const float* x, const float* gamma, void* out_sb, int64_t out_plane, float* out_f32,
+                              int64_t m, int c, float eps, void* stream) {
+    if (!x || !gamma || (c & 3) || c > 1024) return LFDM_E_BADARG;
+    int64_t blocks = (m + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    layernorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, (bf16*)out_sb, out_plane, out_f32, m, c, eps);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}

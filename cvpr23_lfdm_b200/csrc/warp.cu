@@ -1,0 +1,188 @@
+// warp.cu — K12: latent-flow warp + occlusion blend of the LFAE decoder (HBM-bandwidth-bound).
+// One kernel replaces the reference's 7-kernel chain per call site
+//   F.interpolate(flow, bilinear) -> F.grid_sample(bilinear, zeros, align_corners=False) -> F.interpolate(occ) ->
+//   skip*occ + prev*(1-occ)                       (LFAE/modules/generator.py:60-88, call sites :147,149,154,157,162)
+// The 32x32 flow / occlusion latents are up-sampled on the fly (never materialised); the source feature map is
+// channels-last so each bilinear tap is a contiguous float4 run; every output element is written exactly once.
+#include "common.cuh"
+
+namespace {
+
+struct Taps {
+    int x0, x1, y0, y1;          // clamped-valid indices are checked via the v* flags
+    float wnw, wne, wsw, wse;
+    bool vx0, vx1, vy0, vy1;
+};
+
+// torch upsample_bilinear2d, align_corners=False: src = max(0, scale*(dst+0.5)-0.5)
+__device__ __forceinline__ void up_coord(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.f - l1;
+}
+
+__device__ __forceinline__ float bil4(float v00, float v01, float v10, float v11, float lh0, float lh1, float lw0,
+                                      float lw1) {
+    return lh0 * (lw0 * v00 + lw1 * v01) + lh1 * (lw0 * v10 + lw1 * v11);
+}
+
+// flow/occ sampling at output pixel (y,x) of an (hs,ws) map from (hf,wf) latents; returns grid coords + occlusion
+__device__ __forceinline__ void latent_at(const float* __restrict__ flow, const float* __restrict__ occ, int64_t n,
+                                          int y, int x, int hs, int ws, int hf, int wf, float& gx, float& gy,
+                                          float& oc) {
+    int y0, y1, x0, x1;
+    float lh0, lh1, lw0, lw1;
+    up_coord(y, (float)hf / (float)hs, hf, y0, y1, lh0, lh1);
+    up_coord(x, (float)wf / (float)ws, wf, x0, x1, lw0, lw1);
+    const float* f = flow + n * hf * wf * 2;
+    const float2 f00 = *reinterpret_cast<const float2*>(f + (y0 * wf + x0) * 2);
+    const float2 f01 = *reinterpret_cast<const float2*>(f + (y0 * wf + x1) * 2);
+    const float2 f10 = *reinterpret_cast<const float2*>(f + (y1 * wf + x0) * 2);
+    const float2 f11 = *reinterpret_cast<const float2*>(f + (y1 * wf + x1) * 2);
+    gx = bil4(f00.x, f01.x, f10.x, f11.x, lh0, lh1, lw0, lw1);
+    gy = bil4(f00.y, f01.y, f10.y, f11.y, lh0, lh1, lw0, lw1);
+    oc = 1.f;
+    if (occ) {
+        const float* o = occ + n * hf * wf;
+        oc = bil4(o[y0 * wf + x0], o[y0 * wf + x1], o[y1 * wf + x0], o[y1 * wf + x1], lh0, lh1, lw0, lw1);
+    }
+}
+
+// torch grid_sampler_2d bilinear / zeros / align_corners=False
+__device__ __forceinline__ Taps make_taps(float gx, float gy, int hs, int ws) {
+    Taps t;
+    float ix = ((gx + 1.f) * (float)ws - 1.f) / 2.f;
+    float iy = ((gy + 1.f) * (float)hs - 1.f) / 2.f;
+    float fx = floorf(ix), fy = floorf(iy);
+    t.x0 = (int)fx; t.y0 = (int)fy; t.x1 = t.x0 + 1; t.y1 = t.y0 + 1;
+    float ex = fx + 1.f, ey = fy + 1.f;
+    t.wnw = (ex - ix) * (ey - iy);
+    t.wne = (ix - fx) * (ey - iy);
+    t.wsw = (ex - ix) * (iy - fy);
+    t.wse = (ix - fx) * (iy - fy);
+    t.vx0 = t.x0 >= 0 && t.x0 < ws; t.vx1 = t.x1 >= 0 && t.x1 < ws;
+    t.vy0 = t.y0 >= 0 && t.y0 < hs; t.vy1 = t.y1 >= 0 && t.y1 < hs;
+    return t;
+}
+
+__device__ __forceinline__ float4 fma4(float4 acc, float4 v, float w) {
+    acc.x += v.x * w; acc.y += v.y * w; acc.z += v.z * w; acc.w += v.w * w;
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) warp_rows_kernel(const float* __restrict__ src, const float* __restrict__ flow,
+                                                        const float* __restrict__ occ, const float* __restrict__ prev,
+                                                        float* __restrict__ out_f32, bf16* __restrict__ out_sb,
+                                                        int64_t out_plane, const float* __restrict__ sb_scale,
+                                                        const float* __restrict__ sb_shift, int sb_act, int64_t n_img,
+                                                        int frames_per_src, int hs, int ws, int c, int hf, int wf) {
+    const int c4 = c >> 2;
+    const int64_t total = n_img * hs * ws * c4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c4);
+        const int64_t pix = i / c4;
+        const int x = (int)(pix % ws);
+        const int y = (int)((pix / ws) % hs);
+        const int64_t n = pix / ((int64_t)hs * ws);
+        float gx, gy, oc;
+        latent_at(flow, occ, n, y, x, hs, ws, hf, wf, gx, gy, oc);
+        const Taps t = make_taps(gx, gy, hs, ws);
+        const float* sb = src + (n / frames_per_src) * (int64_t)hs * ws * c + cq * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t.vy0 && t.vx0) acc = fma4(acc, *reinterpret_cast<const float4*>(sb + ((int64_t)t.y0 * ws + t.x0) * c), t.wnw);
+        if (t.vy0 && t.vx1) acc = fma4(acc, *reinterpret_cast<const float4*>(sb + ((int64_t)t.y0 * ws + t.x1) * c), t.wne);
+        if (t.vy1 && t.vx0) acc = fma4(acc, *reinterpret_cast<const float4*>(sb + ((int64_t)t.y1 * ws + t.x0) * c), t.wsw);
+        if (t.vy1 && t.vx1) acc = fma4(acc, *reinterpret_cast<const float4*>(sb + ((int64_t)t.y1 * ws + t.x1) * c), t.wse);
+        const int64_t o = pix * c + cq * 4;
+        float4 r;
+        if (occ) {
+            r = make_float4(acc.x * oc, acc.y * oc, acc.z * oc, acc.w * oc);
+            if (prev) {
+                const float4 p = *reinterpret_cast<const float4*>(prev + o);
+                const float om = 1.f - oc;
+                r.x += p.x * om; r.y += p.y * om; r.z += p.z * om; r.w += p.w * om;
+            }
+        } else {
+            r = acc;
+        }
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = r;
+        if (out_sb) {
+            float u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int cc = cq * 4 + e;
+                float v = u[e];
+                if (sb_scale) v *= sb_scale[cc];
+                if (sb_shift) v += sb_shift[cc];
+                u[e] = apply_act(v, sb_act);
+            }
+            store_sb4(out_sb, out_plane, o, make_float4(u[0], u[1], u[2], u[3]));
+        }
+    }
+}
+
+// 3-channel planar image: one thread per output pixel
+__global__ void __launch_bounds__(256) warp_image_kernel(const float* __restrict__ src, const float* __restrict__ flow,
+                                                         const float* __restrict__ occ, const float* __restrict__ prev,
+                                                         int prev_ld, float* __restrict__ out, int b, int f, int h,
+                                                         int w, int hf, int wf) {
+    const int64_t hw = (int64_t)h * w;
+    const int64_t total = (int64_t)b * f * hw;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w);
+        const int y = (int)((i / w) % h);
+        const int64_t n = i / hw;
+        const int bi = (int)(n / f), fi = (int)(n % f);
+        float gx, gy, oc;
+        latent_at(flow, occ, n, y, x, h, w, hf, wf, gx, gy, oc);
+        const Taps t = make_taps(gx, gy, h, w);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* sp = src + ((int64_t)bi * 3 + ch) * hw;
+            float acc = 0.f;
+            if (t.vy0 && t.vx0) acc += sp[(int64_t)t.y0 * w + t.x0] * t.wnw;
+            if (t.vy0 && t.vx1) acc += sp[(int64_t)t.y0 * w + t.x1] * t.wne;
+            if (t.vy1 && t.vx0) acc += sp[(int64_t)t.y1 * w + t.x0] * t.wsw;
+            if (t.vy1 && t.vx1) acc += sp[(int64_t)t.y1 * w + t.x1] * t.wse;
+            float r = acc;
+            if (occ) {
+                r = acc * oc;
+                if (prev) r += prev[i * prev_ld + ch] * (1.f - oc);
+            }
+            out[(((int64_t)bi * 3 + ch) * f + fi) * hw + (int64_t)y * w + x] = r;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int lfdm_warp_blend_rows(const float* src, const float* flow, const float* occ, const float* prev,
+                                    float* out_f32, void* out_sb, int64_t out_plane, const float* sb_scale,
+                                    const float* sb_shift, int sb_act, int n, int frames_per_src, int hs, int ws, int c,
+                                    int hf, int wf, void* stream) {
+    if (!src || !flow || (c & 3) || frames_per_src <= 0 || (!out_f32 && !out_sb)) return LFDM_E_BADARG;
+    int64_t total = (int64_t)n * hs * ws * (c >> 2);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    warp_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, flow, occ, prev, out_f32, (bf16*)out_sb,
+                                                                        out_plane, sb_scale, sb_shift, sb_act, n,
+                                                                        frames_per_src, hs, ws, c, hf, wf);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lfdm_warp_blend_image(const float* src, const float* flow, const float* occ, const float* prev,
+                                     int prev_ld, float* out, int b, int f, int h, int w, int hf, int wf,
+                                     void* stream) {
+    if (!src || !flow || !out) return LFDM_E_BADARG;
+    int64_t total = (int64_t)b * f * h * w;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    warp_image_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, flow, occ, prev, prev_ld, out, b, f, h, w,
+                                                                         hf, wf);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}

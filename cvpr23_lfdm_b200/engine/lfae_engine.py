@@ -1,0 +1,232 @@
+"""LFAE engines — reference `Generator` (LFAE/modules/generator.py), `RegionPredictor`, `BGMotionPredictor` on the
+sm_100a kernels.
+
+Decode data flow (forward_with_flow, generator.py:136-166) with the legal restructurings of SURVEY.md K11-K13:
+  * the frame-invariant encoder (first + down blocks) runs ONCE per source image and its skips are reused by all
+    frames (the reference re-runs it for each of the 40 frames, video_flow_diffusion_model.py:206-214);
+  * all frames of all samples are decoded as one batch (frames are batch items of the row matrices);
+  * eval-mode BatchNorm is folded: post-conv BN into the conv weights/bias, pre-activation BN (+ReLU) of the
+    ResBlocks into the producer's epilogue (sb_scale/sb_shift/sb_act);
+  * nearest x2 up-sampling + 3x3 conv = four 2x2 convs with pre-summed weights (4/9 of the MACs);
+  * every deform_input/apply_optical chain is one warp+blend kernel (csrc/warp.cu).
+"""
+import torch
+from .. import _lib as L
+from .._lib import SB, ptr, stream, check, lib
+from . import ops
+from .ops import ConvLayer, f32
+
+
+def _bn_affine(bn):
+    s = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps))
+    t = bn.bias.detach().float() - bn.running_mean.detach().float() * s
+    return s.contiguous(), t.contiguous()
+
+
+def _fold_post_bn(conv, bn):
+    """conv -> BN(eval): W' = s*W, b' = s*b + t"""
+    s, t = _bn_affine(bn)
+    w = conv.weight.detach().float() * s[:, None, None, None]
+    b = conv.bias.detach().float() * s + t
+    return w, b
+
+
+def _warp_rows(src, flow, occ, prev, out_f32, out_sb, n, fps, hs, ws, c, hf, wf, sb_scale=None, sb_shift=None, sb_act=0):
+    check(lib().lfdm_warp_blend_rows(ptr(src), ptr(flow), ptr(occ), ptr(prev), ptr(out_f32),
+                                     ptr(out_sb.t) if out_sb is not None else None,
+                                     out_sb.plane if out_sb is not None else 0, ptr(sb_scale), ptr(sb_shift), sb_act,
+                                     n, fps, hs, ws, c, hf, wf, stream()), "lfdm_warp_blend_rows")
+
+
+def _warp_image(img, flow, occ, prev, prev_ld, out, b, f, h, w, hf, wf):
+    check(lib().lfdm_warp_blend_image(ptr(img), ptr(flow), ptr(occ), ptr(prev), prev_ld, ptr(out), b, f, h, w, hf, wf,
+                                      stream()), "lfdm_warp_blend_image")
+
+
+class GeneratorEngine:
+    def __init__(self, gen):
+        self.device = gen.final.weight.device
+        dev = self.device
+        if gen.training:
+            # the reference runs the LFAE in eval mode inside FlowDiffusion (video_flow_diffusion_model.py:44,53,60);
+            # batch-statistics BatchNorm (train mode) is a training feature and is not implemented here.
+            pass
+        self.skips_enabled = gen.skips
+        self.nc = gen.num_channels
+        # ---- encoder
+        w, b = _fold_post_bn(gen.first.conv, gen.first.norm)            # (64, 3, 7, 7)
+        self.c0 = w.shape[0]
+        self.k_first = w.shape[-1]
+        kreal = self.k_first * self.k_first * self.nc
+        self.kpad = (kreal + 63) // 64 * 64
+        wflat = torch.zeros(self.c0, self.kpad, device=dev)
+        wflat[:, :kreal] = w.permute(0, 2, 3, 1).reshape(self.c0, kreal)     # k = tap*nc + ch
+        self.first = ConvLayer(wflat.reshape(self.c0, self.kpad, 1, 1), b, name="gen.first")
+        self.downs = []
+        for i, blk in enumerate(gen.down_blocks):
+            w, b = _fold_post_bn(blk.conv, blk.norm)
+            self.downs.append(ConvLayer(w, b, pad=1, name=f"gen.down{i}"))
+        # ---- bottleneck
+        self.res = []
+        blocks = list(gen.bottleneck.children())
+        for i, rb in enumerate(blocks):
+            w1, b1 = _fold_post_bn(rb.conv1, rb.norm2)                   # norm2 follows conv1
+            c1 = ConvLayer(w1, b1, pad=1, name=f"gen.r{i}.conv1")
+            c2 = ConvLayer(rb.conv2.weight.detach().float(), rb.conv2.bias, pad=1, name=f"gen.r{i}.conv2")
+            self.res.append((c1, c2, _bn_affine(rb.norm1)))
+        # ---- decoder
+        self.ups = []
+        for i, blk in enumerate(gen.up_blocks):
+            w, b = _fold_post_bn(blk.conv, blk.norm)
+            self.ups.append(ConvLayer(w, b, mode=L.CONV_UPNEAREST, pad=1, name=f"gen.up{i}"))
+        self.final = ConvLayer(gen.final.weight.detach().float(), gen.final.bias, pad=gen.final.padding[0], name="gen.final")
+        self.has_pfp = gen.pixelwise_flow_predictor is not None
+        self._gen = gen
+        self._pfp = None
+
+    # ------------------------------------------------------------------------------------------------
+    def encode(self, img):
+        """first + down blocks (generator.py:137-141).  img (B, 3, H, W) -> list of (F32 rows, C, h, w) skips"""
+        dev = self.device
+        img = img.float().contiguous()
+        b, c, h, w = img.shape
+        m = b * h * w
+        cols = SB(m, self.kpad, dev)
+        check(lib().lfdm_im2col_small(ptr(img), b, c, 1, h, w, self.k_first, self.k_first // 2, self.kpad, ptr(cols.t),
+                                      cols.plane, stream()), "lfdm_im2col_small")
+        s0, s0_sb = f32(m, self.c0, dev), SB(m, self.c0, dev)
+        self.first([cols], b, h, w, out_f32=s0, out_sb=s0_sb, f32_act=L.ACT_RELU, sb_act=L.ACT_RELU)
+        skips = [(s0, self.c0, h, w)]
+        x_sb, ch, cw = s0_sb, h, w
+        for i, layer in enumerate(self.downs):
+            co = layer.cout
+            y = f32(b * ch * cw, co, dev)
+            layer([x_sb], b, ch, cw, out_f32=y, f32_act=L.ACT_RELU)
+            ch, cw = ch // 2, cw // 2
+            p, p_sb = f32(b * ch * cw, co, dev), SB(b * ch * cw, co, dev)
+            check(lib().lfdm_avgpool2_rows(ptr(y), b, ch * 2, cw * 2, co, ptr(p), ptr(p_sb.t), p_sb.plane, stream()),
+                  "lfdm_avgpool2_rows")
+            skips.append((p, co, ch, cw))
+            x_sb = p_sb
+        return skips
+
+    def compute_fea(self, img):
+        skips = self.encode(img)
+        rows, c, h, w = skips[-1]
+        b = img.shape[0]
+        out = torch.empty((b, c, 1, h * w), device=self.device)
+        ops.from_rows(rows, b, c, 1, h * w, out)
+        return out.reshape(b, c, h, w)
+
+    def decode(self, img, skips, flow, occ, b, f):
+        """flow [N][hf][wf][2] fp32 contiguous, occ [N][hf][wf]; N = b*f frames; returns (prediction, deformed) (B,3,F,H,W)"""
+        dev = self.device
+        n = b * f
+        hf, wf = flow.shape[1], flow.shape[2]
+        _, _, H, W = img.shape
+        img = img.float().contiguous()
+        deformed = torch.empty((b, self.nc, f, H, W), device=dev)
+        _warp_image(img, flow, None, None, 0, deformed, b, f, H, W, hf, wf)
+        src, c, h, w = skips[-1]
+        m = n * h * w
+        # out = warp(skips[-1]) * occ                       (generator.py:149)
+        x = f32(m, c, dev)
+        a = SB(m, c, dev)
+        s1, t1 = self.res[0][2] if self.res else (None, None)
+        _warp_rows(src, flow, occ, None, x, a if self.res else None, n, f, h, w, c, hf, wf, s1, t1, L.ACT_RELU)
+        # bottleneck ResBlock2d x N                          (generator.py:151, util.py:84-92)
+        for i, (c1, c2, _) in enumerate(self.res):
+            a2 = SB(m, c, dev)
+            c1([a], n, h, w, out_sb=a2, sb_act=L.ACT_RELU)
+            x_new = f32(m, c, dev)
+            if i + 1 < len(self.res):
+                sn, tn = self.res[i + 1][2]
+                a_next = SB(m, c, dev)
+                c2([a2], n, h, w, out_f32=x_new, out_sb=a_next, residual=x, sb_scale=sn, sb_shift=tn, sb_act=L.ACT_RELU)
+                a = a_next
+            else:
+                c2([a2], n, h, w, out_f32=x_new, residual=x)
+            x = x_new
+        # up blocks with skip warps                           (generator.py:152-155)
+        prev = x
+        for i, up in enumerate(self.ups):
+            src, c, h, w = skips[-(i + 1)]
+            m = n * h * w
+            if self.skips_enabled:
+                blended = SB(m, c, dev)
+                _warp_rows(src, flow, occ, prev, None, blended, n, f, h, w, c, hf, wf)
+            else:
+                blended = SB(m, c, dev)
+                check(lib().lfdm_split_bf16(ptr(prev), ptr(blended.t), blended.plane, prev.numel(), stream()), "lfdm_split_bf16")
+            co = up.cout
+            y = f32(n * 4 * h * w, co, dev)
+            up([blended], n, h, w, out_f32=y, f32_act=L.ACT_RELU)
+            prev = y
+        src, c, h, w = skips[0]
+        m = n * h * w
+        last = SB(m, c, dev)
+        if self.skips_enabled:
+            _warp_rows(src, flow, occ, prev, None, last, n, f, h, w, c, hf, wf)      # generator.py:157
+        else:
+            check(lib().lfdm_split_bf16(ptr(prev), ptr(last.t), last.plane, prev.numel(), stream()), "lfdm_split_bf16")
+        rgb = f32(m, self.nc, dev)
+        self.final([last], n, h, w, out_f32=rgb, f32_act=L.ACT_SIGMOID)              # generator.py:158-159
+        pred = torch.empty((b, self.nc, f, H, W), device=dev)
+        if self.skips_enabled:
+            _warp_image(img, flow, occ, rgb, self.nc, pred, b, f, H, W, hf, wf)      # generator.py:162
+        else:
+            ops.from_rows(rgb, b, self.nc, f, H * W, pred)
+        return pred, deformed
+
+    # ---- reference API ---------------------------------------------------------------------------------------
+    def forward_with_flow(self, source_image, optical_flow, occlusion_map):
+        b = source_image.shape[0]
+        skips = self.encode(source_image)
+        flow = optical_flow.float().contiguous()
+        occ = occlusion_map.float().contiguous().reshape(b, occlusion_map.shape[-2], occlusion_map.shape[-1])
+        pred, deformed = self.decode(source_image, skips, flow, occ, b, 1)
+        return {"deformed": deformed[:, :, 0], "prediction": pred[:, :, 0]}
+
+    def decode_video(self, source_image, grid, conf):
+        b, _, f, h, w = grid.shape
+        skips = self.encode(source_image)
+        flow = grid.float().permute(0, 2, 3, 4, 1).contiguous().reshape(b * f, h, w, 2)
+        occ = conf.float().permute(0, 2, 1, 3, 4).contiguous().reshape(b * f, h, w)
+        return self.decode(source_image, skips, flow, occ, b, f)
+
+    def forward(self, source_image, driving_region_params, source_region_params, bg_params=None):
+        from .motion_engine import PixelwiseFlowEngine
+        if not self.has_pfp:
+            raise NotImplementedError("Generator without pixelwise_flow_predictor")
+        if self._pfp is None:
+            self._pfp = PixelwiseFlowEngine(self._gen.pixelwise_flow_predictor)
+        b = source_image.shape[0]
+        skips = self.encode(source_image)
+        mp = self._pfp.forward(source_image, driving_region_params, source_region_params, bg_params)
+        flow = mp["optical_flow"]
+        occ = mp["occlusion_map"]
+        pred, deformed = self.decode(source_image, skips, flow.contiguous(),
+                                     occ.reshape(b, occ.shape[-2], occ.shape[-1]).contiguous(), b, 1)
+        rows, c, h, w = skips[-1]
+        fea = torch.empty((b, c, 1, h * w), device=self.device)
+        ops.from_rows(rows, b, c, 1, h * w, fea)
+        return {"bottle_neck_feat": fea.reshape(b, c, h, w), "deformed": deformed[:, :, 0], "optical_flow": flow,
+                "occlusion_map": occ, "prediction": pred[:, :, 0]}
+
+
+class RegionPredictorEngine:
+    def __init__(self, mod):
+        from .motion_engine import RegionEngine
+        self._e = RegionEngine(mod)
+
+    def forward(self, x):
+        return self._e.forward(x)
+
+
+class BGPredictorEngine:
+    def __init__(self, mod):
+        from .motion_engine import BGEngine
+        self._e = BGEngine(mod)
+
+    def forward(self, src, drv):
+        return self._e.forward(src, drv)

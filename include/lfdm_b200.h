@@ -1,0 +1,173 @@
+/*
+ * lfdm_b200.h — C-ABI of liblfdm_b200.so: the sm_100a kernels of the LFDM sampling + LFAE decode hot path.
+ *
+ * The reference (nihaomiao/CVPR23_LFDM) has no FFI layer: its "plugin boundary" for this path is the Python
+ * nn.Module API.  The host-side mirror of that API lives in cvpr23_lfdm_b200/{dm,lfae}/ and calls
+ * ONLY the entry points declared here (through ctypes; INTEGRATION.md shows the binding).  Each entry point cites the
+ * reference call site(s) whose arithmetic it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless it says "host".
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns 0 on success, a
+ *     cudaError_t value (>0) on a CUDA failure, or a negative LFDM_E_* code on an argument error.  No host sync,
+ *     no allocation: all entry points are CUDA-graph capturable.
+ *   - activations are "row matrices": X[M][C], row m = ((n*H + h)*W + w), n = b*F + f (frames are batch items,
+ *     every 3-D conv of the reference has a (1,k,k) kernel).  Two storage formats:
+ *       F32 : float  [M][C]
+ *       SB  : split-bf16, two planes of __nv_bfloat16 [M][C]: hi = bf16(x), lo = bf16(x - hi)   (x ~ hi + lo,
+ *             |err| <= 2^-17 |x|).  SB is what the tcgen05 GEMM consumes; hi*hi + hi*lo + lo*hi in fp32 TMEM
+ *             accumulators reproduces fp32 products to ~2^-16 relative.  `plane` arguments give the element offset
+ *             between the hi and the lo plane.
+ */
+#ifndef LFDM_B200_H
+#define LFDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFDM_E_BADARG   (-1)
+#define LFDM_E_UNSUPP   (-2)   /* shape not supported by the requested engine (caller may use the SIMT engine) */
+#define LFDM_E_NODRIVER (-3)   /* cuTensorMapEncodeTiled not resolvable */
+
+#define LFDM_ENGINE_SIMT 0     /* fp32 CUDA-core implicit GEMM, any shape                                   */
+#define LFDM_ENGINE_TC   1     /* tcgen05 / TMEM / TMA implicit GEMM, split-bf16 x3, power-of-two geometry   */
+
+#define LFDM_ACT_NONE    0
+#define LFDM_ACT_RELU    1
+#define LFDM_ACT_SIGMOID 2
+
+#define LFDM_CONV_DIRECT     0 /* out(ho,wo) += in(ho*s - pad + kh, wo*s - pad + kw)                          */
+#define LFDM_CONV_TRANSPOSED 1 /* ConvTranspose stride 2: in((ho + pad - kh)/2, ...) when divisible           */
+#define LFDM_CONV_UPNEAREST  2 /* nearest x2 upsample then stride-1 conv: in((ho - pad + kh) >> 1, ...)       */
+
+/* One 2-D convolution / GEMM over row matrices, with fused epilogue.
+ * Replaces: nn.Conv3d (1,k,k) / nn.ConvTranspose3d / nn.Conv2d / nn.Linear call sites of
+ *   DM/modules/video_flow_diffusion.py:156-167,199,224,246-247,300-301,410-411,495,508 and
+ *   LFAE/modules/util.py:78-81,102-103,122-123,142-143, LFAE/modules/generator.py:51 (+ folded BatchNorm).
+ * v[m][n] = sum_k A[m][k] W[n][k] + bias[n] + residual[m'][n];   out_f32 = f32_act(v);
+ * out_sb = split(sb_act(sb_scale[n]*v + sb_shift[n]));   gn_stats[b][g] += (sum v, sum v^2)                */
+typedef struct lfdm_conv_desc {
+    /* A operand: up to two sources concatenated along channels (virtual torch.cat, video_flow_diffusion.py:580,587) */
+    const void*  a_sb[2];      /* SB hi plane (or NULL)                                                     */
+    const float* a_f32[2];     /* F32 (or NULL); exactly one of a_sb[i]/a_f32[i] is set for a used source    */
+    int64_t      a_plane[2];   /* SB plane offset in elements                                                */
+    int32_t      a_c[2];       /* channels of each source; a_c[1] = 0 when unused                            */
+    int32_t      nf, h_in, w_in;
+    int32_t      h_out, w_out;
+    int32_t      kh, kw, pad, stride;
+    int32_t      mode;         /* LFDM_CONV_*                                                                 */
+    int32_t      reflect;      /* 1: reflect padding (padding_mode='reflect', video_flow_diffusion.py:162)    */
+    /* weights */
+    const float* w_f32;        /* SIMT: [kh*kw][Cin_total][Cout]                                              */
+    const void*  w_sb;         /* TC  : packed by lfdm_pack, hi plane                         */
+    int64_t      w_plane;
+    const float* bias;         /* [Cout] or NULL                                                              */
+    int32_t      c_out;
+    /* epilogue */
+    const float* residual;     /* F32 [M'][Cout] or NULL                                                      */
+    int32_t      res_bcast_f;  /* >0: residual row = (m / (F*P))*P + m % P with F = res_bcast_f, P = h_out*w_out
+                                  (frame-invariant term, hoisted init_conv(fea) of video_flow_diffusion.py:713-714) */
+    float*       out_f32;      /* or NULL                                                                     */
+    int32_t      f32_act;
+    void*        out_sb;       /* or NULL                                                                     */
+    int64_t      out_plane;
+    int32_t      sb_act;
+    const float* sb_scale;     /* [Cout] or NULL (1)                                                          */
+    const float* sb_shift;     /* [Cout] or NULL (0)                                                          */
+    double*      gn_stats;     /* [B][groups][2] accumulators (pre-zeroed) or NULL (TC engine only)           */
+    int32_t      gn_cpg;       /* channels per group                                                          */
+    int32_t      rows_per_sample;
+} lfdm_conv_desc;
+
+int lfdm_conv(const lfdm_conv_desc* d, int engine, void* stream);
+
+/* --- normalisation ------------------------------------------------------------------------------------------- */
+/* GroupNorm statistics of F32 x[M][C]: stats[b][g] = (sum, sumsq) in double.  video_flow_diffusion.py:200,205 */
+int lfdm_gn_stats(const float* x, int64_t m, int c, int groups, int rows_per_sample, double* stats, void* stream);
+/* y = silu(gn(x)*(scale+1)+shift) (+ residual): Block.forward + ResnetBlock residual, video_flow_diffusion.py:203-211,237.
+ * ss: row b at ss + b*ss_stride holds (scale[C] | shift[C]), or NULL.                                           */
+int lfdm_gn_apply(const float* x, const double* stats, const float* gamma, const float* beta, const float* ss,
+                  int64_t ss_stride, const float* residual, float* out_f32, void* out_sb, int64_t out_plane, int64_t m, int c,
+                  int groups, int rows_per_sample, float eps, void* stream);
+/* channel LayerNorm (biased var, gamma only): video_flow_diffusion.py:176-179 -> SB (and/or F32)              */
+int lfdm_layernorm(const float* x, const float* gamma, void* out_sb, int64_t out_plane, float* out_f32,
+                   int64_t m, int c, float eps, void* stream);
+
+/* --- attention cores ----------------------------------------------------------------------------------------- */
+/* softmax(q k^T * . + bias) v over sequences gathered from qkv[M][3*heads*32].
+ * sequence s: rows base(s) + j*row_stride, j < seq_len, base(s) = (s / inner)*outer_stride + (s % inner)*inner_stride.
+ * rot_cos/rot_sin: [seq_len][16] or NULL; pos_bias: [heads][seq_len][seq_len] or NULL.
+ * Attention.forward video_flow_diffusion.py:303-363 (+ EinopsToAndFrom :270-283).  seq_len <= 64.              */
+int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_seq, int seq_len,
+                      int heads, int64_t inner, int64_t outer_stride, int64_t inner_stride, int64_t row_stride,
+                      const float* rot_cos, const float* rot_sin, const float* pos_bias, void* stream);
+/* SpatialLinearAttention core video_flow_diffusion.py:253-263: per (frame, head) over n = hw positions.        */
+int lfdm_attn_linear(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_frames, int n_pos,
+                     int heads, void* stream);
+
+/* --- embeddings ---------------------------------------------------------------------------------------------- */
+/* y[r][n] = act_out( sum_k act_in(x[r][k]) W[n][k] + b[n] ), small-M GEMV-class (time_mlp :422-428, block mlp :217-220).
+ * act_in/out: 0 none, 1 silu, 2 gelu(erf).                                                                    */
+int lfdm_small_linear(const float* x, const float* w, const float* b, float* y, int rows, int k, int n,
+                      int act_in, int act_out, void* stream);
+/* SinusoidalPosEmb :146-153: out[r] = (sin(t*freqs), cos(t*freqs)); freqs[dim/2] = exp(arange * -log(1e4)/(half-1)) */
+int lfdm_sinusoidal(const int64_t* t, const float* freqs, float* out, int rows, int dim, void* stream);
+/* ss[b][:] = a[a_row(b)][:] + c[b][:]   (time-table row + per-sample cond term)                                 */
+int lfdm_ss_combine(const float* time_tab, const int32_t* step_idx, const float* cond_tab, float* ss, int b, int n,
+                    void* stream);
+
+/* --- sampler (GaussianDiffusion.p_mean_variance / p_sample / ddim_sample, video_flow_diffusion.py:697-746,792-827) */
+/* x0 = c1*x - c2*eps ; absx0 = |x0|.  coef: device table [n_steps][8], row = *step_idx (or 0 if NULL):
+ *   {c1, c2, a, b, sigma, c_eps, ddim, noclip}:  ddim=0: x' = a*x0c + b*x + sigma*z ; ddim=1: x' = a*x0c + c_eps*eps + sigma*z;
+ *   noclip=1 skips the clamp (clip_denoised=False) */
+int lfdm_sampler_x0(const float* x, const float* eps, const float* coef, const int32_t* step_idx, float* absx0,
+                    int64_t n_per_sample, int b, void* stream);
+/* exact torch.quantile(|x0|, q) (linear interpolation) per sample via radix select; s[b] = max(1, quantile).     */
+int lfdm_sampler_quantile(const float* absx0, float* s, int64_t n_per_sample, int b, int64_t k_lo, float w_hi,
+                          void* workspace, void* stream);
+/* x_out = a*clamp(x0,-s,s)/s + b*x + c_eps*eps + sigma*z  (s == NULL: static clamp to [-1,1]); advances *step_idx   */
+int lfdm_sampler_update(const float* x, const float* eps, const float* noise, const float* s, const float* coef,
+                        int32_t* step_idx, int advance, float* x_out, float* x0_out, int64_t n_per_sample, int b,
+                        void* stream);
+
+/* --- LFAE warp / blend (Generator.deform_input + apply_optical, generator.py:60-88) --------------------------- */
+/* out[n][y][x][c] = bilinear_sample(src[n / frames_per_src], up(flow[n]))*up(occ[n]) + prev[n]*(1-up(occ[n]))
+ * src rows F32 [Ns*Hs*Ws][C]; flow [N][hf][wf][2]; occ [N][hf][wf] (NULL: no occlusion); prev F32 rows or NULL.  */
+int lfdm_warp_blend_rows(const float* src, const float* flow, const float* occ, const float* prev, float* out_f32,
+                         void* out_sb, int64_t out_plane, const float* sb_scale, const float* sb_shift, int sb_act,
+                         int n, int frames_per_src, int hs, int ws, int c, int hf, int wf, void* stream);
+/* planar variant for the 3-channel image: src NCHW (Ns,3,H,W); prev rows F32 [N*H*W][prev_ld] (sigmoid output) or NULL;
+ * out NCDHW (B,3,F,H,W) written at [b][c][f].  generator.py:147,162.                                           */
+int lfdm_warp_blend_image(const float* src, const float* flow, const float* occ, const float* prev, int prev_ld,
+                          float* out, int b, int f, int h, int w, int hf, int wf, void* stream);
+
+/* --- layout / small ops -------------------------------------------------------------------------------------- */
+/* in[b][c][f][p] (strides sb, sc, sf, 1) -> rows [(b*F+f)*P + p][c_pad] (zero padded), SB and/or F32.           */
+int lfdm_to_rows(const float* in, int b, int c, int f, int p, int64_t sb, int64_t sc, int64_t sf, int c_pad,
+                 void* out_sb, int64_t out_plane, float* out_f32, void* stream);
+/* rows F32 [(b*F+f)*P+p][ld] (first c channels) -> out[b][c][f][p] contiguous.                                   */
+int lfdm_from_rows(const float* rows, int ld, int b, int c, int f, int p, float* out, void* stream);
+/* 7x7 (k x k) im2col of a few-channel planar tensor in[b][c][f][h][w] -> SB rows [M][k_pad], k = tap*c + ch      */
+int lfdm_im2col_small(const float* in, int b, int c, int f, int h, int w, int ksize, int pad, int k_pad,
+                      void* out_sb, int64_t out_plane, void* stream);
+/* 2x2 average pool on rows (DownBlock2d, util.py:124,131)                                                        */
+int lfdm_avgpool2_rows(const float* in, int n, int h, int w, int c, float* out_f32, void* out_sb, int64_t out_plane,
+                       void* stream);
+/* final 1x1 heads (video_flow_diffusion.py:495,508,588): out[b][0:2|2][f][p] from two F32 row matrices            */
+int lfdm_unet_heads(const float* a, const float* wa, const float* ba, int na, const float* o, const float* wo,
+                    const float* bo, int no, int c, int b, int f, int p, float* out, void* stream);
+
+/* --- weight packing (host-side helper, device pointers) ------------------------------------------------------ */
+/* fp32 [rows][cols] -> SB planes                                                                                 */
+int lfdm_split_bf16(const float* in, void* out_sb, int64_t out_plane, int64_t n, void* stream);
+
+/* library info: returns sm arch the kernels were compiled for (100) and fills `has_tc` with 1                    */
+int lfdm_version(int* arch, int* has_tc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFDM_B200_H */

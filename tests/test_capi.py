@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/lfdm_b200.h declares."""
+import os
+import re
+import ctypes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cvpr23_lfdm_b200.build import build
+    lib_path = build()
+    hdr = open(os.path.join(ROOT, "include", "lfdm_b200.h")).read()
+    declared = sorted(set(re.findall(r"^int (lfdm_[a-z0-9_]+)\(", hdr, flags=re.M)))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/lfdm_b200.h but not exported"
+    from cvpr23_lfdm_b200 import _lib
+    assert sorted(_lib.EXPORTED) == declared
+    arch, tc = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.lib().lfdm_version(ctypes.byref(arch), ctypes.byref(tc))
+    assert arch.value == 100 and tc.value == 1
+
+
+def test_conv_desc_layout_matches_header():
+    """ctypes mirror of lfdm_conv_desc has the same field order as the C struct"""
+    from cvpr23_lfdm_b200._lib import ConvDesc
+    hdr = open(os.path.join(ROOT, "include", "lfdm_b200.h")).read()
+    body = hdr[hdr.index("typedef struct lfdm_conv_desc {"):hdr.index("} lfdm_conv_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for piece in decl.split(","):
+            ident = re.findall(r"([A-Za-z_][A-Za-z_0-9]*)\s*(?:\[\d+\])?\s*$", piece.strip())
+            names.append(ident[-1])
+    assert names == [f[0] for f in ConvDesc._fields_], names
+
+
+def test_product_does_not_import_oracle():
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "cvpr23_lfdm_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M):
+                    bad.append(f)
+    assert not bad
+
+
+def test_no_cpu_fallback():
+    import torch
+    import pytest
+    import cvpr23_lfdm_b200 as P
+    if torch.cuda.is_available():
+        pytest.skip("checks the CPU-side failure mode")
+    u = P.Unet3D(dim=16, cond_dim=8, dim_mults=(1, 2), channels=11, attn_heads=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        u(torch.zeros(1, 11, 2, 8, 8), torch.zeros(1, dtype=torch.long), cond=torch.zeros(1, 8))
