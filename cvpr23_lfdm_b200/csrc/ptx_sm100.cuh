@@ -50,10 +50,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return done != 0;
 }
 // bounded wait: a protocol bug traps (kernel aborts with an error) instead of hanging the GPU
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
+        if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();   // 4 s: protocol bug
     }
 }
 

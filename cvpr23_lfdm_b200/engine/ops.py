@@ -123,6 +123,7 @@ class ConvLayer:
                   out_plane=out_sb.plane if out_sb is not None else 0, sb_act=sb_act, sb_scale=sb_scale,
                   sb_shift=sb_shift, gn_stats=None, gn_cpg=0, rows_per_sample=rows_per_sample)
         rc = L.E_UNSUPP
+        self.last_engine = "simt"
         if self.w_sb is not None and all_sb:
             if fused_stats:
                 cpg = self.cout // gn_groups
@@ -133,7 +134,9 @@ class ConvLayer:
                 else:
                     fused_stats = False
             rc = L.conv(kw, L.ENGINE_TC)
+            self.last_engine = "tc"
             if rc == L.E_UNSUPP:
+                self.last_engine = "simt"
                 kw["gn_stats"] = None
                 fused_stats = False
         else:
