@@ -7,6 +7,9 @@ from .._lib import SB, ptr, stream, check, lib
 # engine policy: "tc" (tcgen05 where the geometry allows, SIMT otherwise), "simt" (force CUDA-core engine)
 DEFAULT_ENGINE = os.environ.get("LFDM_ENGINE", "tc")
 FUSED_GN_STATS = os.environ.get("LFDM_FUSED_GN_STATS", "1") == "1"
+# when set to a list, every conv launch appends (name, engine, algorithmic_flops, start_event, end_event):
+# bench.py uses it for the live CUDA-event roofline measurement (never enabled inside timed regions)
+PROFILE = None
 
 
 def f32(m, c, device):
@@ -124,6 +127,10 @@ class ConvLayer:
                   sb_shift=sb_shift, gn_stats=None, gn_cpg=0, rows_per_sample=rows_per_sample)
         rc = L.E_UNSUPP
         self.last_engine = "simt"
+        ev0 = None
+        if PROFILE is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if self.w_sb is not None and all_sb:
             if fused_stats:
                 cpg = self.cout // gn_groups
@@ -145,6 +152,11 @@ class ConvLayer:
             kw["gn_stats"] = None
             rc = L.conv(kw, L.ENGINE_SIMT)
         check(rc, f"lfdm_conv[{self.name}]")
+        if ev0 is not None:
+            ev1.record()
+            eff_taps = self.kh * self.kw if self.mode == L.CONV_DIRECT else 4   # post-hoist: 2x2 sub-kernels per output
+            flops = 2.0 * nf * ho * wo * self.cout * self.cin * eff_taps
+            PROFILE.append((self.name, self.last_engine, flops, ev0, ev1))
         if gn_stats is not None and not fused_stats:
             assert out_f32 is not None
             check(lib().lfdm_gn_stats(ptr(out_f32), out_f32.shape[0], self.cout, gn_groups, rows_per_sample,

@@ -147,11 +147,15 @@ class SamplerEngine:
         graphable = USE_GRAPH and g.noise_fn is None
         n = len(times)
         i = 0
+        calls0 = L.launch_count
+        self.last_stats = {"steps": n, "calls_per_step": 0, "other_calls": 0}
         if graphable and n >= 4:
             # leading steps run eagerly (also warms every kernel / allocator pool), then one graph per noise pattern
             noise_buf = torch.empty(shape, device=dev)
             while i < 2:
+                c0 = L.launch_count
                 step(g._randn(shape, dev) if draw_noise[i] else None)
+                self.last_stats["calls_per_step"] = L.launch_count - c0
                 i += 1
             graph = None
             while i < n:
@@ -169,7 +173,9 @@ class SamplerEngine:
                 i += 1
             return img
         while i < n:
+            c0 = L.launch_count
             step(g._randn(shape, dev) if draw_noise[i] else None)
+            self.last_stats["calls_per_step"] = L.launch_count - c0
             i += 1
         return img
 

@@ -283,7 +283,8 @@ def test_small_linear_and_sinusoidal():
     half = dim // 2
     fr = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1))).float()
     out = torch.empty(5, dim, device=dev())
-    check(lib().lfdm_sinusoidal(ptr(t.to(dev())), ptr(fr.to(dev())), ptr(out), 5, dim, stream()), "sinusoidal")
+    td, frd = t.to(dev()), fr.to(dev())     # keep the device copies alive across the async launch
+    check(lib().lfdm_sinusoidal(ptr(td), ptr(frd), ptr(out), 5, dim, stream()), "sinusoidal")
     close(out, O.sinusoidal_emb(t, dim), "sinusoidal", rtol=1e-4, atol=1e-5)
 
 
@@ -331,7 +332,8 @@ def test_sampler_quantile_ties_and_ddim():
     for q in (0.9, 0.5, 0.999):
         r = torch.tensor(q, dtype=torch.float32) * (n_per - 1)
         k_lo, w_hi = int(torch.floor(r).item()), float((r - torch.floor(r)).item())
-        check(lib().lfdm_sampler_quantile(ptr(a.to(dev())), ptr(s), n_per, b, k_lo, w_hi, None, stream()), "quantile")
+        a_d = a.to(dev())
+        check(lib().lfdm_sampler_quantile(ptr(a_d), ptr(s), n_per, b, k_lo, w_hi, None, stream()), "quantile")
         assert torch.equal(s.cpu(), torch.quantile(a, q, dim=-1).clamp(min=1.0))
     buf = O.diffusion_buffers(1000)
     x, eps, z = [torch.randn(b, n_per, generator=g) for _ in range(3)]
@@ -418,7 +420,8 @@ def test_layout_kernels():
     # im2col (7x7, pad 3) vs unfold
     x3 = torch.randn(2, 3, 2, 8, 8, generator=g)
     cols = SB(2 * 2 * 64, 192, dev())
-    check(lib().lfdm_im2col_small(ptr(x3.to(dev())), 2, 3, 2, 8, 8, 7, 3, 192, ptr(cols.t), cols.plane, stream()), "im2col")
+    x3d = x3.to(dev())
+    check(lib().lfdm_im2col_small(ptr(x3d), 2, 3, 2, 8, 8, 7, 3, 192, ptr(cols.t), cols.plane, stream()), "im2col")
     xf = x3.permute(0, 2, 1, 3, 4).reshape(4, 3, 8, 8)
     un = F.unfold(xf, 7, padding=3).reshape(4, 3, 49, 64).permute(0, 3, 2, 1).reshape(4 * 64, 147)   # k = tap*3 + ch
     got = cols.float().cpu()
@@ -427,13 +430,15 @@ def test_layout_kernels():
     # avgpool
     y = torch.randn(3, 8, 6, 4, generator=g)          # (n, c, h, w)
     pooled = torch.empty(3 * 3 * 2, 8, device=dev())
-    check(lib().lfdm_avgpool2_rows(ptr(rows_of(y).to(dev())), 3, 6, 4, 8, ptr(pooled), None, 0, stream()), "avgpool")
+    yd = rows_of(y).to(dev())
+    check(lib().lfdm_avgpool2_rows(ptr(yd), 3, 6, 4, 8, ptr(pooled), None, 0, stream()), "avgpool")
     close(pooled, rows_of(F.avg_pool2d(y, 2)), "avgpool", rtol=1e-5, atol=1e-6)
     # heads
     a, o = torch.randn(2 * 3 * 16, 16, generator=g), torch.randn(2 * 3 * 16, 16, generator=g)
     wa, ba, wo, bo = torch.randn(2, 16, generator=g), torch.randn(2, generator=g), torch.randn(1, 16, generator=g), torch.randn(1, generator=g)
     outh = torch.empty(2, 3, 3, 4, 4, device=dev())
-    check(lib().lfdm_unet_heads(ptr(a.to(dev())), ptr(wa.to(dev())), ptr(ba.to(dev())), 2, ptr(o.to(dev())), ptr(wo.to(dev())),
-                                ptr(bo.to(dev())), 1, 16, 2, 3, 16, ptr(outh), stream()), "heads")
+    ad, wad, bad, od, wod, bod = [v.to(dev()) for v in (a, wa, ba, o, wo, bo)]
+    check(lib().lfdm_unet_heads(ptr(ad), ptr(wad), ptr(bad), 2, ptr(od), ptr(wod), ptr(bod), 1, 16, 2, 3, 16, ptr(outh),
+                                stream()), "heads")
     ref = torch.cat([F.linear(a, wa, ba), F.linear(o, wo, bo)], 1).reshape(2, 3, 16, 3).permute(0, 3, 1, 2).reshape(2, 3, 3, 4, 4)
     close(outh, ref, "heads", rtol=1e-4, atol=1e-5)
