@@ -160,6 +160,25 @@ int lfdm_avgpool2_rows(const float* in, int n, int h, int w, int c, float* out_f
 int lfdm_unet_heads(const float* a, const float* wa, const float* ba, int na, const float* o, const float* wo,
                     const float* bo, int no, int c, int b, int f, int p, float* out, void* stream);
 
+/* --- full-LFAE branch: dense motion / regions --------------------------------------- */
+/* AntiAliasInterpolation2d (LFAE/modules/util.py:256-264): depthwise ks x ks Gaussian (zero pad ka) + ::s subsample, NCHW */
+int lfdm_antialias_down(const float* in, const float* kern, float* out, int n, int c, int h, int w, int ks, int ka,
+                        int s, void* stream);
+/* RegionPredictor head (region_predictor.py:84-117): logits rows [(n*hw+p)][K] -> heatmap (N,K,h,w), shift (N,K,2),
+ * covar/affine/u/d (N,K,2,2); the 2x2 SVD is closed form on the device (replaces torch.svd(covar.cpu()), :21).  */
+int lfdm_region_moments(const float* logits, int n, int k, int h, int w, float temperature, float* heatmap,
+                        float* shift, float* covar, float* affine, float* u, float* d, void* stream);
+/* PixelwiseFlowPredictor front half (pixelwise_flow_predictor.py:48-102): hourglass input rows [N*hw][(K+1)*(nch+1)]
+ * (heatmap difference | deformed source per region) and sparse motions (N,K+1,h,w,2).                            */
+int lfdm_motion_prep(const float* down, const float* d_shift, const float* d_covar, const float* d_affine,
+                     const float* s_shift, const float* s_covar, const float* s_affine, const float* bg, int n, int k,
+                     int nch, int h, int w, int revert_axis_swap, float* hg_in, float* sparse, void* stream);
+/* back half (:124-135): softmax over the K+1 mask logits, flow = sum_k mask_k * sparse_k, occlusion = sigmoid      */
+int lfdm_motion_finish(const float* logits, int ld, const float* sparse, int n, int k, int hw, int has_occ,
+                       float* flow, float* occ, void* stream);
+/* per-image mean over positions of a row matrix [N*p][c] -> [N][c] (bg_motion_predictor.py:47)                    */
+int lfdm_rows_mean(const float* rows, int n, int p, int c, float* out, void* stream);
+
 /* --- weight packing (host-side helper, device pointers) ------------------------------------------------------ */
 /* fp32 [rows][cols] -> SB planes                                                                                 */
 int lfdm_split_bf16(const float* in, void* out_sb, int64_t out_plane, int64_t n, void* stream);

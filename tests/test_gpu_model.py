@@ -189,3 +189,33 @@ def test_cuda_graph_loop_equals_eager(full_model):
         outs.append(gd.sample(fea, cond=cond, cond_scale=1.0).clone())
     SE.USE_GRAPH = True
     close(outs[1], outs[0], "graph vs eager", rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ full-LFAE branch
+def test_tiny_generator_forward_and_predictors_match_reference_golden(golden):
+    """Generator.forward (dense motion network), RegionPredictor, BGMotionPredictor vs the reference goldens.
+    RegionPredictor's `affine` = U*sqrt(S) is compared up to the per-column sign of U (the reference's LAPACK SVD
+    sign is data dependent; region_predictor.py:21) plus the invariant affine @ affine^T == covar."""
+    import cvpr23_lfdm_b200 as P
+    g = golden("tiny_lfae.pt")
+    gen = P.Generator(**g["gen_cfg"])
+    gen.load_state_dict(g["gen_sd"])
+    gen = gen.cuda().eval()
+    cu = lambda d: {k: v.cuda() for k, v in d.items()}
+    out = gen(g["img"].cuda(), source_region_params=cu(g["src_rp"]), driving_region_params=cu(g["drv_rp"]), bg_params=g["bg"].cuda())
+    for k in ("optical_flow", "occlusion_map", "deformed", "prediction", "bottle_neck_feat"):
+        close(out[k], g["full"][k], f"Generator.forward {k}")
+    rp = P.RegionPredictor(**g["rp_cfg"])
+    rp.load_state_dict(g["rp_sd"])
+    rp = rp.cuda().eval()
+    r = rp(g["img"].cuda())
+    for k in ("shift", "covar", "heatmap"):
+        close(r[k], g["src_rp"][k], f"RegionPredictor {k}", rtol=1e-3, atol=2e-4)
+    a, ref = r["affine"].cpu(), g["src_rp"]["affine"]
+    close(a @ a.transpose(-1, -2), g["src_rp"]["covar"], "affine affine^T == covar", rtol=2e-3, atol=2e-4)
+    sign = torch.sign((a * ref).sum(dim=-2, keepdim=True))           # per-column sign alignment
+    close(a * sign, ref, "RegionPredictor affine (up to column sign)", rtol=5e-3, atol=1e-3)
+    bg = P.BGMotionPredictor(**g["bg_cfg"])
+    bg.load_state_dict(g["bg_sd"])
+    bg = bg.cuda().eval()
+    close(bg(g["img"].cuda(), g["drv"].cuda()), g["bg"], "BGMotionPredictor")
