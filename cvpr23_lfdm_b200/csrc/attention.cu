@@ -17,92 +17,168 @@ namespace {
 constexpr int DH = 32;
 constexpr int MAXL = 64;
 
-// one warp per (sequence, head); 4 warps per block
+// one warp per (sequence, head).  Register-tiled: lane (a = lane/8, b = lane%8) owns score rows i = a + 4r and
+// columns j = b + 8c (RIP x CJ accumulators), so every smem operand fetched with one LDS.128 feeds RIP*CJ*4/(RIP+CJ)
+// FMAs instead of one; P is staged through smem once and P.V is tiled the same way (rows i, 4 consecutive d per lane).
+constexpr int QP = DH + 4;     // smem row pitch (floats): 16-byte aligned rows, conflict-free LDS.128 over 8 rows
+
+template <int RIP, int CJ>
 __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
                                                            int64_t out_plane, float* __restrict__ out_f32,
                                                            int64_t n_seq, int L, int heads, int64_t inner,
                                                            int64_t outer_stride, int64_t inner_stride,
                                                            int64_t row_stride, const float* __restrict__ rot_cos,
                                                            const float* __restrict__ rot_sin,
-                                                           const float* __restrict__ pos_bias) {
-    extern __shared__ float s_dyn[];   // [4 warps][3][L][DH+1]
+                                                           const float* __restrict__ pos_bias, int warps_per_block) {
+    extern __shared__ __align__(16) float s_dyn[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float (*sq)[DH + 1] = reinterpret_cast<float (*)[DH + 1]>(s_dyn + (size_t)(w * 3 + 0) * L * (DH + 1));
-    float (*sk)[DH + 1] = reinterpret_cast<float (*)[DH + 1]>(s_dyn + (size_t)(w * 3 + 1) * L * (DH + 1));
-    float (*sv)[DH + 1] = reinterpret_cast<float (*)[DH + 1]>(s_dyn + (size_t)(w * 3 + 2) * L * (DH + 1));
-    const int64_t unit = (int64_t)blockIdx.x * 4 + w;
-    if (unit >= n_seq * heads) return;   // whole warp exits together (no block-level sync below)
+    const int LP = CJ * 8;                 // padded sequence length (multiple of 8, >= L)
+    const int PP = LP + 4;                 // P row pitch
+    float* sq = s_dyn + (size_t)w * (3 * LP * QP + LP * PP);
+    float* sk = sq + LP * QP;
+    float* sv = sk + LP * QP;
+    float* sp = sv + LP * QP;
+    const int64_t unit = (int64_t)blockIdx.x * warps_per_block + w;
+    if (unit >= n_seq * heads) return;     // whole warp exits together (only __syncwarp below)
     const int64_t s = unit / heads;
     const int h = (int)(unit - s * heads);
     const int hid = heads * DH;
     const int64_t base = (s / inner) * outer_stride + (s % inner) * inner_stride;
-    const float scale = 0.17677669529663687f;  // 32^-0.5 (python float dim_head ** -0.5 rounded to fp32)
+    const float scale = 0.17677669529663687f;  // 32^-0.5
 
-    // load q (scaled, rotated), k (rotated), v: lane = d
-    for (int j = 0; j < L; ++j) {
-        const float* r = qkv + (base + (int64_t)j * row_stride) * (3 * hid) + h * DH;
-        float q = r[lane] * scale, k = r[hid + lane], v = r[2 * hid + lane];
-        if (rot_cos) {
-            // interleaved pairs (2p, 2p+1): rot(x)[2p] = -x[2p+1], rot(x)[2p+1] = x[2p]
-            float c = rot_cos[j * (DH / 2) + (lane >> 1)], sn = rot_sin[j * (DH / 2) + (lane >> 1)];
-            float qo = __shfl_xor_sync(0xffffffffu, q, 1), ko = __shfl_xor_sync(0xffffffffu, k, 1);
-            float qr = (lane & 1) ? qo : -qo, kr = (lane & 1) ? ko : -ko;
-            q = q * c + qr * sn;
-            k = k * c + kr * sn;
+    for (int j = 0; j < LP; ++j) {
+        float q = 0.f, k = 0.f, v = 0.f;
+        if (j < L) {
+            const float* r = qkv + (base + (int64_t)j * row_stride) * (3 * hid) + h * DH;
+            q = r[lane] * scale; k = r[hid + lane]; v = r[2 * hid + lane];
+            if (rot_cos) {
+                // interleaved pairs (2p, 2p+1): rot(x)[2p] = -x[2p+1], rot(x)[2p+1] = x[2p]
+                float c = rot_cos[j * (DH / 2) + (lane >> 1)], sn = rot_sin[j * (DH / 2) + (lane >> 1)];
+                float qo = __shfl_xor_sync(0xffffffffu, q, 1), ko = __shfl_xor_sync(0xffffffffu, k, 1);
+                float qr = (lane & 1) ? qo : -qo, kr = (lane & 1) ? ko : -ko;
+                q = q * c + qr * sn;
+                k = k * c + kr * sn;
+            }
         }
-        sq[j][lane] = q; sk[j][lane] = k; sv[j][lane] = v;
+        sq[j * QP + lane] = q; sk[j * QP + lane] = k; sv[j * QP + lane] = v;
     }
     __syncwarp();
 
+    const int a = lane >> 3, b = lane & 7;
     const float* pb = pos_bias ? pos_bias + (int64_t)h * L * L : nullptr;
-    for (int i = 0; i < L; ++i) {
-        // scores for columns lane and lane+32
-        float s0 = -INFINITY, s1 = -INFINITY;
-        if (lane < L) {
-            float a = 0.f;
+    for (int i0 = 0; i0 < L; i0 += 4 * RIP) {
+        // ---- S = Q K^T for rows i0 + a + 4r, columns b + 8c
+        float acc[RIP][CJ];
 #pragma unroll
-            for (int d = 0; d < DH; ++d) a = fmaf(sq[i][d], sk[lane][d], a);
-            if (pb) a += pb[i * L + lane];
-            s0 = a;
-        }
-        if (lane + 32 < L) {
-            float a = 0.f;
+        for (int r = 0; r < RIP; ++r)
 #pragma unroll
-            for (int d = 0; d < DH; ++d) a = fmaf(sq[i][d], sk[lane + 32][d], a);
-            if (pb) a += pb[i * L + lane + 32];
-            s1 = a;
+            for (int c = 0; c < CJ; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
+        for (int d = 0; d < DH; d += 4) {
+            float4 kq[CJ];
+#pragma unroll
+            for (int c = 0; c < CJ; ++c) kq[c] = *reinterpret_cast<const float4*>(sk + (b + 8 * c) * QP + d);
+#pragma unroll
+            for (int r = 0; r < RIP; ++r) {
+                int i = i0 + a + 4 * r;
+                i = i < LP ? i : LP - 1;
+                const float4 qv = *reinterpret_cast<const float4*>(sq + i * QP + d);
+#pragma unroll
+                for (int c = 0; c < CJ; ++c) {
+                    acc[r][c] = fmaf(qv.x, kq[c].x, acc[r][c]);
+                    acc[r][c] = fmaf(qv.y, kq[c].y, acc[r][c]);
+                    acc[r][c] = fmaf(qv.z, kq[c].z, acc[r][c]);
+                    acc[r][c] = fmaf(qv.w, kq[c].w, acc[r][c]);
+                }
+            }
         }
-        float mx = warp_max(fmaxf(s0, s1));
-        float p0 = (lane < L) ? expf(s0 - mx) : 0.f;
-        float p1 = (lane + 32 < L) ? expf(s1 - mx) : 0.f;
-        float den = warp_sum(p0 + p1);
-        float inv = 1.f / den;
-        p0 *= inv; p1 *= inv;
-        float o = 0.f;
-        const int l0 = L < 32 ? L : 32;
-        for (int j = 0; j < l0; ++j) o = fmaf(__shfl_sync(0xffffffffu, p0, j), sv[j][lane], o);
-        for (int j = 32; j < L; ++j) o = fmaf(__shfl_sync(0xffffffffu, p1, j - 32), sv[j][lane], o);
-        int64_t orow = base + (int64_t)i * row_stride;
-        int64_t oi = orow * hid + h * DH + lane;
-        if (out_f32) out_f32[oi] = o;
-        if (out_sb) store_sb1(out_sb, out_plane, oi, o);
+        // ---- bias, row softmax (a row lives in the 8 lanes that share `a`), P -> smem
+#pragma unroll
+        for (int r = 0; r < RIP; ++r) {
+            const int i = i0 + a + 4 * r;
+            const bool row_ok = i < L;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < CJ; ++c) {
+                const int j = b + 8 * c;
+                float v = acc[r][c];
+                if (pb && row_ok && j < L) v += pb[i * L + j];
+                v = (j < L) ? v : -INFINITY;
+                acc[r][c] = v;
+                mx = fmaxf(mx, v);
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < CJ; ++c) {
+                float e = expf(acc[r][c] - mx);      // exp(-inf) = 0 for padded columns
+                acc[r][c] = e;
+                sum += e;
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+            const float inv = 1.f / sum;
+            if (i < LP) {
+#pragma unroll
+                for (int c = 0; c < CJ; ++c) sp[i * PP + b + 8 * c] = acc[r][c] * inv;
+            }
+        }
+        __syncwarp();
+        // ---- O = P V for rows i0 + a + 4r, columns d = 4b .. 4b+3
+        float4 o[RIP];
+#pragma unroll
+        for (int r = 0; r < RIP; ++r) o[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < LP; j += 4) {
+            const float4 v0 = *reinterpret_cast<const float4*>(sv + (j + 0) * QP + 4 * b);
+            const float4 v1 = *reinterpret_cast<const float4*>(sv + (j + 1) * QP + 4 * b);
+            const float4 v2 = *reinterpret_cast<const float4*>(sv + (j + 2) * QP + 4 * b);
+            const float4 v3 = *reinterpret_cast<const float4*>(sv + (j + 3) * QP + 4 * b);
+#pragma unroll
+            for (int r = 0; r < RIP; ++r) {
+                int i = i0 + a + 4 * r;
+                i = i < LP ? i : LP - 1;
+                const float4 p = *reinterpret_cast<const float4*>(sp + i * PP + j);
+                o[r].x = fmaf(p.x, v0.x, o[r].x); o[r].y = fmaf(p.x, v0.y, o[r].y); o[r].z = fmaf(p.x, v0.z, o[r].z); o[r].w = fmaf(p.x, v0.w, o[r].w);
+                o[r].x = fmaf(p.y, v1.x, o[r].x); o[r].y = fmaf(p.y, v1.y, o[r].y); o[r].z = fmaf(p.y, v1.z, o[r].z); o[r].w = fmaf(p.y, v1.w, o[r].w);
+                o[r].x = fmaf(p.z, v2.x, o[r].x); o[r].y = fmaf(p.z, v2.y, o[r].y); o[r].z = fmaf(p.z, v2.z, o[r].z); o[r].w = fmaf(p.z, v2.w, o[r].w);
+                o[r].x = fmaf(p.w, v3.x, o[r].x); o[r].y = fmaf(p.w, v3.y, o[r].y); o[r].z = fmaf(p.w, v3.z, o[r].z); o[r].w = fmaf(p.w, v3.w, o[r].w);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RIP; ++r) {
+            const int i = i0 + a + 4 * r;
+            if (i < L) {
+                const int64_t oi = (base + (int64_t)i * row_stride) * hid + h * DH + 4 * b;
+                if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi) = o[r];
+                if (out_sb) store_sb4(out_sb, out_plane, oi, o[r]);
+            }
+        }
+        __syncwarp();
     }
 }
 
-// one block (256 threads, 8 warps) per (frame, head)
-__global__ void __launch_bounds__(256, 3) attn_linear_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
-                                                          int64_t out_plane, float* __restrict__ out_f32, int n_pos,
-                                                          int heads) {
+// one block (256 threads, 8 warps) per (frame, head).  Each warp walks 32-row chunks: the exp / softmax of a row is
+// computed once by lane = d and staged in a per-warp smem tile; the 32x32 context (and its application to q) is
+// register-tiled: lane (a = lane/8, b = lane%8) owns ctx[d = 8a..8a+7][e = 4b..4b+3].
+__global__ void __launch_bounds__(256, 2) attn_linear_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
+                                                             int64_t out_plane, float* __restrict__ out_f32, int n_pos,
+                                                             int heads) {
+    constexpr int TP = DH + 4;                           // tile row pitch
+    __shared__ __align__(16) float s_buf[8 * 32 * TP];   // per-warp chunk tiles; aliased by the cross-warp reduction
     __shared__ float s_red[8][DH];
     __shared__ float s_max[DH];
-    __shared__ float s_ctx[8][DH][DH + 1];
-    __shared__ float s_ctxn[DH][DH + 1];
+    __shared__ __align__(16) float s_ctxn[DH][DH + 4];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = lane >> 3, b = lane & 7;
     const int64_t fr = blockIdx.x / heads;
     const int h = blockIdx.x % heads;
     const int hid = heads * DH;
     const float* base = qkv + fr * n_pos * (int64_t)(3 * hid) + h * DH;
     const float scale = 0.17677669529663687f;
+    float* tile = s_buf + w * 32 * TP;
 
     // phase 1: column max of k over positions (lane = d)
     float mx = -INFINITY;
@@ -118,52 +194,129 @@ __global__ void __launch_bounds__(256, 3) attn_linear_kernel(const float* __rest
     __syncthreads();
     const float kmax = s_max[lane];
 
-    // phase 2: ctx[d][e] = sum_n exp(k[n][d]-max_d) v[n][e];  den[d] = sum_n exp(k[n][d]-max_d)
-    float ctx[DH];
+    // phase 2: ctx[d][e] += exp(k[n][d] - max_d) * v[n][e];  den[d] += exp(..)
+    float ctx[8][4];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) ctx[d] = 0.f;
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ctx[i][j] = 0.f;
     float den = 0.f;
-    for (int n = w; n < n_pos; n += 8) {
-        const float* r = base + (int64_t)n * 3 * hid;
-        float ek = expf(r[hid + lane] - kmax);
-        float v = r[2 * hid + lane];
-        den += ek;
+    const int n_chunks = (n_pos + 31) / 32;
+    for (int c = w; c < n_chunks; c += 8) {
+        const int n0 = c * 32;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const int n = n0 + r;
+            float ek = 0.f;
+            if (n < n_pos) ek = expf(base[(int64_t)n * 3 * hid + hid + lane] - kmax);
+            den += ek;
+            tile[r * TP + lane] = ek;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const int n = n0 + r;
+            if (n >= n_pos) break;                      // warp-uniform
+            const float4 e0 = *reinterpret_cast<const float4*>(tile + r * TP + 8 * a);
+            const float4 e1 = *reinterpret_cast<const float4*>(tile + r * TP + 8 * a + 4);
+            const float4 v = *reinterpret_cast<const float4*>(base + (int64_t)n * 3 * hid + 2 * hid + 4 * b);
+            const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-        for (int d = 0; d < DH; ++d) ctx[d] = fmaf(__shfl_sync(0xffffffffu, ek, d), v, ctx[d]);
+            for (int i = 0; i < 8; ++i) {
+                ctx[i][0] = fmaf(ev[i], v.x, ctx[i][0]); ctx[i][1] = fmaf(ev[i], v.y, ctx[i][1]);
+                ctx[i][2] = fmaf(ev[i], v.z, ctx[i][2]); ctx[i][3] = fmaf(ev[i], v.w, ctx[i][3]);
+            }
+        }
+        __syncwarp();
     }
+    __syncthreads();                                     // all warps done with their tiles: alias s_buf as [8][32][32]
+    float* s_ctx = s_buf;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) s_ctx[w][d][lane] = ctx[d];
+    for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(s_ctx + (w * DH + 8 * a + i) * DH + 4 * b) = make_float4(ctx[i][0], ctx[i][1], ctx[i][2], ctx[i][3]);
     s_red[w][lane] = den;
     __syncthreads();
-    // reduce across the 8 warps: thread t handles entries t, t+256, ... of the 32x32 ctx
     for (int i = threadIdx.x; i < DH * DH; i += 256) {
-        int d = i / DH, e = i % DH;
-        float a = 0.f, dd = 0.f;
+        const int d = i / DH, e = i % DH;
+        float acc = 0.f, dd = 0.f;
 #pragma unroll
-        for (int ww = 0; ww < 8; ++ww) { a += s_ctx[ww][d][e]; dd += s_red[ww][d]; }
-        s_ctxn[d][e] = a / dd;   // softmax normalisation of k folded into the context
+        for (int ww = 0; ww < 8; ++ww) { acc += s_ctx[(ww * DH + d) * DH + e]; dd += s_red[ww][d]; }
+        s_ctxn[d][e] = acc / dd;                         // softmax normalisation of k folded into the context
     }
     __syncthreads();
 #pragma unroll
-    for (int d = 0; d < DH; ++d) ctx[d] = s_ctxn[d][lane];
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(&s_ctxn[8 * a + i][4 * b]);
+        ctx[i][0] = t.x; ctx[i][1] = t.y; ctx[i][2] = t.z; ctx[i][3] = t.w;
+    }
 
     // phase 3: out[n][e] = sum_d ctxn[d][e] * softmax_d(q[n])[d] * scale
-    for (int n = w; n < n_pos; n += 8) {
-        float q = base[(int64_t)n * 3 * hid + lane];
-        float m = warp_max(q);
-        float eq = expf(q - m);
-        float s = warp_sum(eq);
-        float qs = eq / s * scale;
-        float o = 0.f;
+    for (int c = w; c < n_chunks; c += 8) {
+        const int n0 = c * 32;
+#pragma unroll 2
+        for (int r = 0; r < 32; ++r) {
+            const int n = n0 + r;
+            float q = (n < n_pos) ? base[(int64_t)n * 3 * hid + lane] : 0.f;
+            const float m = warp_max(q);
+            const float eq = expf(q - m);
+            const float sm = warp_sum(eq);
+            tile[r * TP + lane] = eq / sm * scale;
+        }
+        __syncwarp();
+#pragma unroll 2
+        for (int r = 0; r < 32; ++r) {
+            const int n = n0 + r;
+            if (n >= n_pos) break;
+            const float4 q0 = *reinterpret_cast<const float4*>(tile + r * TP + 8 * a);
+            const float4 q1 = *reinterpret_cast<const float4*>(tile + r * TP + 8 * a + 4);
+            const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int d = 0; d < DH; ++d) o = fmaf(ctx[d], __shfl_sync(0xffffffffu, qs, d), o);
-        int64_t oi = (fr * n_pos + n) * hid + h * DH + lane;
-        if (out_f32) out_f32[oi] = o;
-        if (out_sb) store_sb1(out_sb, out_plane, oi, o);
+            for (int i = 0; i < 8; ++i) {
+                o.x = fmaf(ctx[i][0], qv[i], o.x); o.y = fmaf(ctx[i][1], qv[i], o.y);
+                o.z = fmaf(ctx[i][2], qv[i], o.z); o.w = fmaf(ctx[i][3], qv[i], o.w);
+            }
+            // reduce over the four d-blocks (lanes that share b)
+            o.x += __shfl_xor_sync(0xffffffffu, o.x, 8);  o.y += __shfl_xor_sync(0xffffffffu, o.y, 8);
+            o.z += __shfl_xor_sync(0xffffffffu, o.z, 8);  o.w += __shfl_xor_sync(0xffffffffu, o.w, 8);
+            o.x += __shfl_xor_sync(0xffffffffu, o.x, 16); o.y += __shfl_xor_sync(0xffffffffu, o.y, 16);
+            o.z += __shfl_xor_sync(0xffffffffu, o.z, 16); o.w += __shfl_xor_sync(0xffffffffu, o.w, 16);
+            if (a == 0) {
+                const int64_t oi = (fr * n_pos + n) * hid + h * DH + 4 * b;
+                if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi) = o;
+                if (out_sb) store_sb4(out_sb, out_plane, oi, o);
+            }
+        }
+        __syncwarp();
     }
 }
 
 }  // namespace
+
+template <int RIP, int CJ>
+static int launch_attn_softmax(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_seq, int seq_len,
+                               int heads, int64_t inner, int64_t outer_stride, int64_t inner_stride, int64_t row_stride,
+                               const float* rot_cos, const float* rot_sin, const float* pos_bias, cudaStream_t st) {
+    const int LP = CJ * 8;
+    const size_t per_warp = sizeof(float) * (size_t)(3 * LP * QP + LP * (LP + 4));
+    int wpb = (int)(100 * 1024 / per_warp);
+    if (wpb > 4) wpb = 4;
+    if (wpb < 1) wpb = 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_softmax_kernel<RIP, CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(per_warp * 4 > 200 * 1024 ? 200 * 1024 : per_warp * 4));
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int64_t units = n_seq * heads;
+    const int64_t blocks = (units + wpb - 1) / wpb;
+    attn_softmax_kernel<RIP, CJ><<<(unsigned)blocks, 32 * wpb, per_warp * wpb, st>>>(
+        qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride, row_stride,
+        rot_cos, rot_sin, pos_bias, wpb);
+    LFDM_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_seq,
                                  int seq_len, int heads, int64_t inner, int64_t outer_stride, int64_t inner_stride,
@@ -171,21 +324,12 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
                                  void* stream) {
     if (!qkv || seq_len <= 0 || seq_len > MAXL || heads <= 0 || inner <= 0) return LFDM_E_BADARG;
     if ((rot_cos == nullptr) != (rot_sin == nullptr)) return LFDM_E_BADARG;
-    int64_t units = n_seq * heads;
-    int64_t blocks = (units + 3) / 4;
-    size_t smem = sizeof(float) * 4 * 3 * (size_t)seq_len * (DH + 1);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(sizeof(float) * 4 * 3 * MAXL * (DH + 1)));
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    attn_softmax_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(
-        qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride, row_stride,
-        rot_cos, rot_sin, pos_bias);
-    LFDM_CHECK_LAUNCH();
-    return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define LFDM_ATTN_ARGS qkv, out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride, row_stride, rot_cos, rot_sin, pos_bias, st
+    if (seq_len <= 16) return launch_attn_softmax<4, 2>(LFDM_ATTN_ARGS);
+    if (seq_len <= 40) return launch_attn_softmax<10, 5>(LFDM_ATTN_ARGS);
+    return launch_attn_softmax<8, 8>(LFDM_ATTN_ARGS);        // L <= 64: two row passes of 32
+#undef LFDM_ATTN_ARGS
 }
 
 extern "C" int lfdm_attn_linear(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_frames,

@@ -24,6 +24,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;               // bf16 elements per K block = 128 bytes = one swizzle row
 constexpr int A_BYTES = BM * BK * 2; // 16 KiB per plane
 constexpr int MAX_TAPS = 52;
+constexpr int NUM_THREADS = 384;     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
 
 struct TcArgs {
     CUtensorMap tmA[8];              // [source*4 + parity view]
@@ -51,8 +52,97 @@ struct TcArgs {
     int64_t rows_per_sample;
 };
 
+// epilogue of 16 accumulator columns [nb, nb+16) of one output row
+__device__ __forceinline__ void epi_chunk16(const TcArgs& a, const uint32_t (&rr)[16], int nb, int64_t orow, int64_t rrow,
+                                            int bsample, int lane, bool vec_ok) {
+    if (nb >= a.c_out) return;       // warp-uniform (padded N)
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+        const bool full = vec_ok && (nb + 16 <= a.c_out);
+        if (full) {
+            if (a.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 b4 = *reinterpret_cast<const float4*>(a.bias + nb + j);
+                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
+            }
+            if (a.residual) {
+                const float* rp = a.residual + rrow * a.c_out + nb;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+                    v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+                }
+            }
+            if (a.gn_stats) {
+                // 16 columns = two 8-column halves; cpg is a multiple of 8
+                float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s0 += v[j]; q0 = fmaf(v[j], v[j], q0); }
+#pragma unroll
+                for (int j = 8; j < 16; ++j) { s1 += v[j]; q1 = fmaf(v[j], v[j], q1); }
+                s0 = warp_sum(s0); q0 = warp_sum(q0); s1 = warp_sum(s1); q1 = warp_sum(q1);
+                if (lane == 0) {
+                    const int g0 = nb / a.gn_cpg, g1 = (nb + 8) / a.gn_cpg;
+                    double* st = a.gn_stats + (int64_t)bsample * a.gn_groups * 2;
+                    if (g0 == g1) {
+                        atomicAdd(st + g0 * 2, (double)s0 + (double)s1);
+                        atomicAdd(st + g0 * 2 + 1, (double)q0 + (double)q1);
+                    } else {
+                        atomicAdd(st + g0 * 2, (double)s0); atomicAdd(st + g0 * 2 + 1, (double)q0);
+                        atomicAdd(st + g1 * 2, (double)s1); atomicAdd(st + g1 * 2 + 1, (double)q1);
+                    }
+                }
+            }
+            const int64_t o = orow * a.c_out + nb;
+            if (a.out_f32) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 o4 = make_float4(apply_act(v[j], a.f32_act), apply_act(v[j + 1], a.f32_act),
+                                            apply_act(v[j + 2], a.f32_act), apply_act(v[j + 3], a.f32_act));
+                    *reinterpret_cast<float4*>(a.out_f32 + o + j) = o4;
+                }
+            }
+            if (a.out_sb) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float u[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float t = v[j + e];
+                        if (a.sb_scale) t *= a.sb_scale[nb + j + e];
+                        if (a.sb_shift) t += a.sb_shift[nb + j + e];
+                        u[e] = apply_act(t, a.sb_act);
+                    }
+                    store_sb4(a.out_sb, a.out_plane, o + j, make_float4(u[0], u[1], u[2], u[3]));
+                }
+            }
+        } else {
+            // ragged N (e.g. Cout = 3): scalar, masked
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = nb + j;
+                if (n < a.c_out) {
+                    float t = v[j];
+                    if (a.bias) t += a.bias[n];
+                    if (a.residual) t += a.residual[rrow * a.c_out + n];
+                    const int64_t o = orow * a.c_out + n;
+                    if (a.out_f32) a.out_f32[o] = apply_act(t, a.f32_act);
+                    if (a.out_sb) {
+                        float u = t;
+                        if (a.sb_scale) u *= a.sb_scale[n];
+                        if (a.sb_shift) u += a.sb_shift[n];
+                        store_sb1(a.out_sb, a.out_plane, o, apply_act(u, a.sb_act));
+                    }
+                }
+            }
+        }
+}
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -75,7 +165,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     }
     if (warp == 1 && ptx::elect_one()) {
         for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 128); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], NUM_THREADS - 128); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -157,7 +247,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int q = warp - 4;              // == warp % 4: TMEM lane quarter this warp may access
+        const int q = warp & 3;              // TMEM lane quarter this warp may access (warp % 4)
+        const int half = (warp - 4) >> 2;    // which column half of the tile this warp drains
         const int r = q * 32 + lane;         // tile row handled by this thread
         const bool vec_ok = (a.c_out % 16) == 0;
         int it = 0;
@@ -180,95 +271,25 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             ptx::mbar_wait(&tfull_bar[as], aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            constexpr int EPI_SPLIT = (BN >= 32) ? 2 : 1;          // column halves handled by warps 4-7 / 8-11
+            constexpr int WCOLS = BN / EPI_SPLIT;
+            const int col0 = (EPI_SPLIT == 2) ? half * WCOLS : 0;
+            if (EPI_SPLIT == 2 || half == 0) {
+                if constexpr (WCOLS >= 32) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t rr[16];
-                ptx::tmem_ld16(taddr + c0, rr);
-                ptx::tmem_ld_wait();
-                const int nb = n0 + c0;
-                if (nb >= a.c_out) continue;       // warp-uniform (padded N)
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
-                const bool full = vec_ok && (nb + 16 <= a.c_out);
-                if (full) {
-                    if (a.bias) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 b4 = *reinterpret_cast<const float4*>(a.bias + nb + j);
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                        }
-                    }
-                    if (a.residual) {
-                        const float* rp = a.residual + rrow * a.c_out + nb;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-                            v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-                        }
-                    }
-                    if (a.gn_stats) {
-                        // 16 columns = two 8-column halves; cpg is a multiple of 8
-                        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { s0 += v[j]; q0 = fmaf(v[j], v[j], q0); }
-#pragma unroll
-                        for (int j = 8; j < 16; ++j) { s1 += v[j]; q1 = fmaf(v[j], v[j], q1); }
-                        s0 = warp_sum(s0); q0 = warp_sum(q0); s1 = warp_sum(s1); q1 = warp_sum(q1);
-                        if (lane == 0) {
-                            const int g0 = nb / a.gn_cpg, g1 = (nb + 8) / a.gn_cpg;
-                            double* st = a.gn_stats + (int64_t)bsample * a.gn_groups * 2;
-                            if (g0 == g1) {
-                                atomicAdd(st + g0 * 2, (double)s0 + (double)s1);
-                                atomicAdd(st + g0 * 2 + 1, (double)q0 + (double)q1);
-                            } else {
-                                atomicAdd(st + g0 * 2, (double)s0); atomicAdd(st + g0 * 2 + 1, (double)q0);
-                                atomicAdd(st + g1 * 2, (double)s1); atomicAdd(st + g1 * 2 + 1, (double)q1);
-                            }
-                        }
-                    }
-                    const int64_t o = orow * a.c_out + nb;
-                    if (a.out_f32) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 o4 = make_float4(apply_act(v[j], a.f32_act), apply_act(v[j + 1], a.f32_act),
-                                                    apply_act(v[j + 2], a.f32_act), apply_act(v[j + 3], a.f32_act));
-                            *reinterpret_cast<float4*>(a.out_f32 + o + j) = o4;
-                        }
-                    }
-                    if (a.out_sb) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float u[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float t = v[j + e];
-                                if (a.sb_scale) t *= a.sb_scale[nb + j + e];
-                                if (a.sb_shift) t += a.sb_shift[nb + j + e];
-                                u[e] = apply_act(t, a.sb_act);
-                            }
-                            store_sb4(a.out_sb, a.out_plane, o + j, make_float4(u[0], u[1], u[2], u[3]));
-                        }
+                    for (int c0 = 0; c0 < WCOLS; c0 += 32) {
+                        uint32_t r0[16], r1[16];
+                        ptx::tmem_ld16(taddr + col0 + c0, r0);
+                        ptx::tmem_ld16(taddr + col0 + c0 + 16, r1);
+                        ptx::tmem_ld_wait();
+                        epi_chunk16(a, r0, n0 + col0 + c0, orow, rrow, bsample, lane, vec_ok);
+                        epi_chunk16(a, r1, n0 + col0 + c0 + 16, orow, rrow, bsample, lane, vec_ok);
                     }
                 } else {
-                    // ragged N (e.g. Cout = 3): scalar, masked
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = nb + j;
-                        if (n < a.c_out) {
-                            float t = v[j];
-                            if (a.bias) t += a.bias[n];
-                            if (a.residual) t += a.residual[rrow * a.c_out + n];
-                            const int64_t o = orow * a.c_out + n;
-                            if (a.out_f32) a.out_f32[o] = apply_act(t, a.f32_act);
-                            if (a.out_sb) {
-                                float u = t;
-                                if (a.sb_scale) u *= a.sb_scale[n];
-                                if (a.sb_shift) u += a.sb_shift[n];
-                                store_sb1(a.out_sb, a.out_plane, o, apply_act(u, a.sb_act));
-                            }
-                        }
-                    }
+                    uint32_t r0[16];
+                    ptx::tmem_ld16(taddr + col0, r0);
+                    ptx::tmem_ld_wait();
+                    epi_chunk16(a, r0, n0 + col0, orow, rrow, bsample, lane, vec_ok);
                 }
             }
             ptx::tc_fence_before();
@@ -335,7 +356,7 @@ int launch(const TcArgs& a, cudaStream_t st) {
     }
     int total = a.m_tiles * a.n_tiles;
     int grid = total < num_sms ? total : num_sms;
-    conv_tc_kernel<BN, STAGES><<<grid, 256, SMEM, st>>>(a);
+    conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, SMEM, st>>>(a);
     LFDM_CHECK_LAUNCH();
     return 0;
 }
