@@ -64,13 +64,30 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def usable_cores():
+    """cores this process may really use: min(affinity mask, cgroup cpu quota) — os.cpu_count() over-counts in containers"""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 def cpu_baseline(threads=None):
     """The reference's CPU arithmetic (oracle port, bit-exact vs the reference on this path) on a bounded sample:
-    B=1, 2 UNet evals + compute_fea + 2 decoded frames; extrapolated to 1000 DDPM steps + 40 frames."""
+    B=1, F=8-frame probe first; if the box is fast enough 2 full 40-frame UNet evals, else the probe scaled by 5;
+    + compute_fea + 2 decoded frames; extrapolated to 1000 DDPM steps + 40 frames."""
     import torch
     import cvpr23_lfdm_b200 as P
     from oracle import lfdm_oracle as O
-    threads = threads or os.cpu_count()
+    threads = threads or usable_cores()
     torch.set_num_threads(threads)
     torch.manual_seed(1234)
     m = P.FlowDiffusion(is_train=False, sampling_timesteps=1000, img_size=32, num_frames=FRAMES,
@@ -84,14 +101,24 @@ def cpu_baseline(threads=None):
         t_fea = time.perf_counter() - t0
         x = torch.randn(1, 3, FRAMES, 32, 32)
         fea5 = skips[-1].unsqueeze(2).repeat(1, 1, FRAMES, 1, 1)
-        O.unet3d_forward(usd, torch.cat([x, fea5], 1), torch.tensor([999]), cond)         # warm-up
-        ts = []
-        for i in range(2):
-            t0 = time.perf_counter()
-            eps = O.unet3d_forward(usd, torch.cat([x, fea5], 1), torch.tensor([998 - i]), cond)
-            x = O.p_sample_step(O.diffusion_buffers(1000), x, 998 - i, eps, torch.randn_like(x))
-            ts.append(time.perf_counter() - t0)
-        t_step = min(ts)
+        # probe: 8 of the 40 frames (the UNet is linear in F except the 40x40 temporal attention, <4 % of the FLOPs)
+        xp = torch.cat([x, fea5], 1)[:, :, :8].contiguous()
+        O.unet3d_forward(usd, xp, torch.tensor([999]), cond)                               # warm-up
+        t0 = time.perf_counter()
+        O.unet3d_forward(usd, xp, torch.tensor([999]), cond)
+        t_probe = time.perf_counter() - t0
+        how = "2 full 40-frame UNet evals + sampler steps"
+        if t_probe * 5 < 8.0:
+            ts = []
+            for i in range(2):
+                t0 = time.perf_counter()
+                eps = O.unet3d_forward(usd, torch.cat([x, fea5], 1), torch.tensor([998 - i]), cond)
+                x = O.p_sample_step(O.diffusion_buffers(1000), x, 998 - i, eps, torch.randn_like(x))
+                ts.append(time.perf_counter() - t0)
+            t_step = min(ts)
+        else:
+            t_step = t_probe * 5
+            how = "one 8-frame UNet eval scaled x5 (box too slow for full evals inside the time bound)"
         flow, occ = x[:, :2, 0].permute(0, 2, 3, 1).contiguous(), (x[:, 2:3, 0] + 1) * 0.5
         t0 = time.perf_counter()
         for _ in range(2):
@@ -99,7 +126,7 @@ def cpu_baseline(threads=None):
         t_frame = (time.perf_counter() - t0) / 2
     total = t_fea + 1000 * t_step + FRAMES * t_frame
     return dict(value=FRAMES / total, unit="frames/s", cores=threads, kind="port",
-                sample=f"B=1: 2 UNet evals+sampler steps ({t_step:.2f} s each), compute_fea ({t_fea:.2f} s), 2 decoded frames "
+                sample=f"B=1: {how} ({t_step:.2f} s per 40-frame step), compute_fea ({t_fea:.2f} s), 2 decoded frames "
                        f"({t_frame:.3f} s each); extrapolated to 1000 DDPM steps + 40 frames = {total:.0f} s/video",
                 t_step=t_step, t_frame=t_frame, t_fea=t_fea)
 

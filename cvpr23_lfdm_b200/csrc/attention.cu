@@ -17,6 +17,14 @@ namespace {
 constexpr int DH = 32;
 constexpr int MAXL = 64;
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // one warp per (sequence, head).  Register-tiled: lane (a = lane/8, b = lane%8) owns score rows i = a + 4r and
 // columns j = b + 8c (RIP x CJ accumulators), so every smem operand fetched with one LDS.128 feeds RIP*CJ*4/(RIP+CJ)
 // FMAs instead of one; P is staged through smem once and P.V is tiled the same way (rows i, 4 consecutive d per lane).
@@ -46,21 +54,40 @@ __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restri
     const int64_t base = (s / inner) * outer_stride + (s % inner) * inner_stride;
     const float scale = 0.17677669529663687f;  // 32^-0.5
 
-    for (int j = 0; j < LP; ++j) {
-        float q = 0.f, k = 0.f, v = 0.f;
-        if (j < L) {
-            const float* r = qkv + (base + (int64_t)j * row_stride) * (3 * hid) + h * DH;
-            q = r[lane] * scale; k = r[hid + lane]; v = r[2 * hid + lane];
-            if (rot_cos) {
-                // interleaved pairs (2p, 2p+1): rot(x)[2p] = -x[2p+1], rot(x)[2p+1] = x[2p]
-                float c = rot_cos[j * (DH / 2) + (lane >> 1)], sn = rot_sin[j * (DH / 2) + (lane >> 1)];
-                float qo = __shfl_xor_sync(0xffffffffu, q, 1), ko = __shfl_xor_sync(0xffffffffu, k, 1);
-                float qr = (lane & 1) ? qo : -qo, kr = (lane & 1) ? ko : -ko;
-                q = q * c + qr * sn;
-                k = k * c + kr * sn;
-            }
+    // gather: 3 tensors x L rows x 8 segments of 16 B, all in flight at once (cp.async), pad rows zeroed
+    {
+        const int nseg = 3 * L * 8;
+        for (int idx = lane; idx < nseg; idx += 32) {
+            const int t = idx / (L * 8);
+            const int rem = idx - t * (L * 8);
+            const int j = rem >> 3, seg = rem & 7;
+            const float* src = qkv + (base + (int64_t)j * row_stride) * (3 * hid) + t * hid + h * DH + seg * 4;
+            cp_async16(sq + t * LP * QP + j * QP + seg * 4, src);
         }
-        sq[j * QP + lane] = q; sk[j * QP + lane] = k; sv[j * QP + lane] = v;
+        cp_async_commit();
+        for (int idx = lane; idx < 3 * (LP - L) * 8; idx += 32) {
+            const int t = idx / ((LP - L) * 8);
+            const int rem = idx - t * ((LP - L) * 8);
+            const int j = L + (rem >> 3), seg = rem & 7;
+            *reinterpret_cast<float4*>(sq + t * LP * QP + j * QP + seg * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        // q *= scale; rotary on interleaved pairs (2p, 2p+1): x' = x c - y s, y' = y c + x s   (reference :325-331)
+        for (int idx = lane; idx < L * (DH / 2); idx += 32) {
+            const int j = idx >> 4, pr = idx & 15;
+            float2 q2 = *reinterpret_cast<float2*>(sq + j * QP + 2 * pr);
+            q2.x *= scale; q2.y *= scale;
+            if (rot_cos) {
+                const float c = rot_cos[j * (DH / 2) + pr], sn = rot_sin[j * (DH / 2) + pr];
+                float2 k2 = *reinterpret_cast<float2*>(sk + j * QP + 2 * pr);
+                const float qx = q2.x * c - q2.y * sn, qy = q2.y * c + q2.x * sn;
+                const float kx = k2.x * c - k2.y * sn, ky = k2.y * c + k2.x * sn;
+                q2 = make_float2(qx, qy);
+                *reinterpret_cast<float2*>(sk + j * QP + 2 * pr) = make_float2(kx, ky);
+            }
+            *reinterpret_cast<float2*>(sq + j * QP + 2 * pr) = q2;
+        }
     }
     __syncwarp();
 
@@ -160,15 +187,27 @@ __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restri
     }
 }
 
-// one block (256 threads, 8 warps) per (frame, head).  Each warp walks 32-row chunks: the exp / softmax of a row is
-// computed once by lane = d and staged in a per-warp smem tile; the 32x32 context (and its application to q) is
+// one block (4 warps) per (frame, head).  Every warp streams 32-row chunks of (k, v) and later q through a
+// double-buffered cp.async pipeline (all bytes of the next chunk are in flight while the current one is consumed);
+// exp / softmax of a row is computed once and kept in the smem tile; the 32x32 context and its application to q are
 // register-tiled: lane (a = lane/8, b = lane%8) owns ctx[d = 8a..8a+7][e = 4b..4b+3].
-__global__ void __launch_bounds__(256, 2) attn_linear_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
-                                                             int64_t out_plane, float* __restrict__ out_f32, int n_pos,
-                                                             int heads) {
-    constexpr int TP = DH + 4;                           // tile row pitch
-    __shared__ __align__(16) float s_buf[8 * 32 * TP];   // per-warp chunk tiles; aliased by the cross-warp reduction
-    __shared__ float s_red[8][DH];
+constexpr int LW = 4;
+constexpr int TP = DH + 4;                               // tile row pitch (floats), rows 16-byte aligned
+constexpr int TILE = 32 * TP;                            // one 32-row tile
+
+__device__ __forceinline__ void issue_rows(float* dst, const float* src_col, int64_t ld, int n0, int n_pos, int lane) {
+    // 32 rows x 8 segments of 16 B
+    for (int idx = lane; idx < 32 * 8; idx += 32) {
+        const int r = idx >> 3, seg = idx & 7;
+        if (n0 + r < n_pos) cp_async16(dst + r * TP + seg * 4, src_col + (int64_t)(n0 + r) * ld + seg * 4);
+    }
+}
+
+__global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
+                                                                 int64_t out_plane, float* __restrict__ out_f32, int n_pos,
+                                                                 int heads) {
+    extern __shared__ __align__(16) float s_dynl[];      // [LW][2 stages][2 tiles][32][TP]; aliased by the reduction
+    __shared__ float s_red[LW][DH];
     __shared__ float s_max[DH];
     __shared__ __align__(16) float s_ctxn[DH][DH + 4];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -176,19 +215,21 @@ __global__ void __launch_bounds__(256, 2) attn_linear_kernel(const float* __rest
     const int64_t fr = blockIdx.x / heads;
     const int h = blockIdx.x % heads;
     const int hid = heads * DH;
-    const float* base = qkv + fr * n_pos * (int64_t)(3 * hid) + h * DH;
+    const int64_t ld = 3 * hid;
+    const float* base = qkv + fr * n_pos * ld + h * DH;
     const float scale = 0.17677669529663687f;
-    float* tile = s_buf + w * 32 * TP;
+    float* wbuf = s_dynl + w * 4 * TILE;                  // stage s: k/q tile at wbuf + s*2*TILE, v tile at + TILE
 
     // phase 1: column max of k over positions (lane = d)
     float mx = -INFINITY;
-    for (int n = w; n < n_pos; n += 8) mx = fmaxf(mx, base[(int64_t)n * 3 * hid + hid + lane]);
+#pragma unroll 16
+    for (int n = w; n < n_pos; n += LW) mx = fmaxf(mx, base[(int64_t)n * ld + hid + lane]);
     s_red[w][lane] = mx;
     __syncthreads();
     if (w == 0) {
         float m = s_red[0][lane];
 #pragma unroll
-        for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[i][lane]);
+        for (int i = 1; i < LW; ++i) m = fmaxf(m, s_red[i][lane]);
         s_max[lane] = m;
     }
     __syncthreads();
@@ -202,24 +243,37 @@ __global__ void __launch_bounds__(256, 2) attn_linear_kernel(const float* __rest
         for (int j = 0; j < 4; ++j) ctx[i][j] = 0.f;
     float den = 0.f;
     const int n_chunks = (n_pos + 31) / 32;
-    for (int c = w; c < n_chunks; c += 8) {
+    if (w < n_chunks) {
+        issue_rows(wbuf, base + hid, ld, w * 32, n_pos, lane);
+        issue_rows(wbuf + TILE, base + 2 * hid, ld, w * 32, n_pos, lane);
+    }
+    cp_async_commit();
+    int st = 0;
+    for (int c = w; c < n_chunks; c += LW, st ^= 1) {
+        const int cn = c + LW;
+        if (cn < n_chunks) {
+            issue_rows(wbuf + (st ^ 1) * 2 * TILE, base + hid, ld, cn * 32, n_pos, lane);
+            issue_rows(wbuf + (st ^ 1) * 2 * TILE + TILE, base + 2 * hid, ld, cn * 32, n_pos, lane);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        float* kt = wbuf + st * 2 * TILE;
+        const float* vt = kt + TILE;
         const int n0 = c * 32;
-#pragma unroll 4
+#pragma unroll 8
         for (int r = 0; r < 32; ++r) {
-            const int n = n0 + r;
-            float ek = 0.f;
-            if (n < n_pos) ek = expf(base[(int64_t)n * 3 * hid + hid + lane] - kmax);
-            den += ek;
-            tile[r * TP + lane] = ek;
+            const float e = (n0 + r < n_pos) ? expf(kt[r * TP + lane] - kmax) : 0.f;
+            den += e;
+            kt[r * TP + lane] = e;
         }
         __syncwarp();
+        const int rows = min(32, n_pos - n0);
 #pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-            const int n = n0 + r;
-            if (n >= n_pos) break;                      // warp-uniform
-            const float4 e0 = *reinterpret_cast<const float4*>(tile + r * TP + 8 * a);
-            const float4 e1 = *reinterpret_cast<const float4*>(tile + r * TP + 8 * a + 4);
-            const float4 v = *reinterpret_cast<const float4*>(base + (int64_t)n * 3 * hid + 2 * hid + 4 * b);
+        for (int r = 0; r < rows; ++r) {
+            const float4 e0 = *reinterpret_cast<const float4*>(kt + r * TP + 8 * a);
+            const float4 e1 = *reinterpret_cast<const float4*>(kt + r * TP + 8 * a + 4);
+            const float4 v = *reinterpret_cast<const float4*>(vt + r * TP + 4 * b);
             const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -229,18 +283,19 @@ __global__ void __launch_bounds__(256, 2) attn_linear_kernel(const float* __rest
         }
         __syncwarp();
     }
-    __syncthreads();                                     // all warps done with their tiles: alias s_buf as [8][32][32]
-    float* s_ctx = s_buf;
+    cp_async_wait<0>();
+    __syncthreads();                                     // all tiles consumed: alias the buffer as [LW][32][32]
+    float* s_ctx = s_dynl;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
         *reinterpret_cast<float4*>(s_ctx + (w * DH + 8 * a + i) * DH + 4 * b) = make_float4(ctx[i][0], ctx[i][1], ctx[i][2], ctx[i][3]);
     s_red[w][lane] = den;
     __syncthreads();
-    for (int i = threadIdx.x; i < DH * DH; i += 256) {
+    for (int i = threadIdx.x; i < DH * DH; i += 32 * LW) {
         const int d = i / DH, e = i % DH;
         float acc = 0.f, dd = 0.f;
 #pragma unroll
-        for (int ww = 0; ww < 8; ++ww) { acc += s_ctx[(ww * DH + d) * DH + e]; dd += s_red[ww][d]; }
+        for (int ww = 0; ww < LW; ++ww) { acc += s_ctx[(ww * DH + d) * DH + e]; dd += s_red[ww][d]; }
         s_ctxn[d][e] = acc / dd;                         // softmax normalisation of k folded into the context
     }
     __syncthreads();
@@ -251,24 +306,42 @@ __global__ void __launch_bounds__(256, 2) attn_linear_kernel(const float* __rest
     }
 
     // phase 3: out[n][e] = sum_d ctxn[d][e] * softmax_d(q[n])[d] * scale
-    for (int c = w; c < n_chunks; c += 8) {
+    if (w < n_chunks) issue_rows(wbuf, base, ld, w * 32, n_pos, lane);
+    cp_async_commit();
+    st = 0;
+    for (int c = w; c < n_chunks; c += LW, st ^= 1) {
+        const int cn = c + LW;
+        if (cn < n_chunks) issue_rows(wbuf + (st ^ 1) * 2 * TILE, base, ld, cn * 32, n_pos, lane);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        float* qt = wbuf + st * 2 * TILE;
         const int n0 = c * 32;
-#pragma unroll 2
-        for (int r = 0; r < 32; ++r) {
-            const int n = n0 + r;
-            float q = (n < n_pos) ? base[(int64_t)n * 3 * hid + lane] : 0.f;
-            const float m = warp_max(q);
-            const float eq = expf(q - m);
-            const float sm = warp_sum(eq);
-            tile[r * TP + lane] = eq / sm * scale;
+        if (n0 + lane < n_pos) {                          // one thread per row: softmax over d, * scale
+            float4 x[8];
+            float m = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                x[i] = *reinterpret_cast<const float4*>(qt + lane * TP + 4 * i);
+                m = fmaxf(m, fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w)));
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                x[i].x = expf(x[i].x - m); x[i].y = expf(x[i].y - m); x[i].z = expf(x[i].z - m); x[i].w = expf(x[i].w - m);
+                sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+            }
+            const float inv = scale / sum;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(qt + lane * TP + 4 * i) = make_float4(x[i].x * inv, x[i].y * inv, x[i].z * inv, x[i].w * inv);
         }
         __syncwarp();
+        const int rows = min(32, n_pos - n0);
 #pragma unroll 2
-        for (int r = 0; r < 32; ++r) {
-            const int n = n0 + r;
-            if (n >= n_pos) break;
-            const float4 q0 = *reinterpret_cast<const float4*>(tile + r * TP + 8 * a);
-            const float4 q1 = *reinterpret_cast<const float4*>(tile + r * TP + 8 * a + 4);
+        for (int r = 0; r < rows; ++r) {
+            const float4 q0 = *reinterpret_cast<const float4*>(qt + r * TP + 8 * a);
+            const float4 q1 = *reinterpret_cast<const float4*>(qt + r * TP + 8 * a + 4);
             const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -282,13 +355,14 @@ __global__ void __launch_bounds__(256, 2) attn_linear_kernel(const float* __rest
             o.x += __shfl_xor_sync(0xffffffffu, o.x, 16); o.y += __shfl_xor_sync(0xffffffffu, o.y, 16);
             o.z += __shfl_xor_sync(0xffffffffu, o.z, 16); o.w += __shfl_xor_sync(0xffffffffu, o.w, 16);
             if (a == 0) {
-                const int64_t oi = (fr * n_pos + n) * hid + h * DH + 4 * b;
+                const int64_t oi = (fr * n_pos + n0 + r) * hid + h * DH + 4 * b;
                 if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi) = o;
                 if (out_sb) store_sb4(out_sb, out_plane, oi, o);
             }
         }
         __syncwarp();
     }
+    cp_async_wait<0>();
 }
 
 }  // namespace
@@ -335,8 +409,15 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
 extern "C" int lfdm_attn_linear(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_frames,
                                 int n_pos, int heads, void* stream) {
     if (!qkv || n_pos <= 0 || heads <= 0) return LFDM_E_BADARG;
-    attn_linear_kernel<<<(unsigned)(n_frames * heads), 256, 0, (cudaStream_t)stream>>>(qkv, (bf16*)out_sb, out_plane,
-                                                                                     out_f32, n_pos, heads);
+    const size_t smem = sizeof(float) * LW * 4 * TILE;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    attn_linear_kernel<<<(unsigned)(n_frames * heads), 32 * LW, smem, (cudaStream_t)stream>>>(qkv, (bf16*)out_sb, out_plane,
+                                                                                             out_f32, n_pos, heads);
     LFDM_CHECK_LAUNCH();
     return 0;
 }
