@@ -30,7 +30,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // FMAs instead of one; P is staged through smem once and P.V is tiled the same way (rows i, 4 consecutive d per lane).
 constexpr int QP = DH + 4;     // smem row pitch (floats): 16-byte aligned rows, conflict-free LDS.128 over 8 rows
 
-template <int RIP, int CJ>
+template <int RIP, int CJ, bool ALIAS_P>   // ALIAS_P: single row pass -> P may overwrite the dead Q/K tiles
 __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
                                                            int64_t out_plane, float* __restrict__ out_f32,
                                                            int64_t n_seq, int L, int heads, int64_t inner,
@@ -42,10 +42,10 @@ __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restri
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int LP = CJ * 8;                 // padded sequence length (multiple of 8, >= L)
     const int PP = LP + 4;                 // P row pitch
-    float* sq = s_dyn + (size_t)w * (3 * LP * QP + LP * PP);
+    float* sq = s_dyn + (size_t)w * (3 * LP * QP + (ALIAS_P ? 0 : LP * PP));
     float* sk = sq + LP * QP;
     float* sv = sk + LP * QP;
-    float* sp = sv + LP * QP;
+    float* sp = ALIAS_P ? sq : sv + LP * QP;
     const int64_t unit = (int64_t)blockIdx.x * warps_per_block + w;
     if (unit >= n_seq * heads) return;     // whole warp exits together (only __syncwarp below)
     const int64_t s = unit / heads;
@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restri
                 }
             }
         }
+        if (ALIAS_P) __syncwarp();      // every lane is done reading Q/K before P overwrites them
         // ---- bias, row softmax (a row lives in the 8 lanes that share `a`), P -> smem
 #pragma unroll
         for (int r = 0; r < RIP; ++r) {
@@ -367,25 +368,26 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
 
 }  // namespace
 
-template <int RIP, int CJ>
+template <int RIP, int CJ, bool ALIAS_P>
 static int launch_attn_softmax(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_seq, int seq_len,
                                int heads, int64_t inner, int64_t outer_stride, int64_t inner_stride, int64_t row_stride,
                                const float* rot_cos, const float* rot_sin, const float* pos_bias, cudaStream_t st) {
     const int LP = CJ * 8;
-    const size_t per_warp = sizeof(float) * (size_t)(3 * LP * QP + LP * (LP + 4));
+    static_assert(!ALIAS_P || (LP * (LP + 4) <= 2 * LP * QP), "P must fit in the Q+K tiles");
+    const size_t per_warp = sizeof(float) * (size_t)(3 * LP * QP + (ALIAS_P ? 0 : LP * (LP + 4)));
     int wpb = (int)(100 * 1024 / per_warp);
     if (wpb > 4) wpb = 4;
     if (wpb < 1) wpb = 1;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_softmax_kernel<RIP, CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(attn_softmax_kernel<RIP, CJ, ALIAS_P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(per_warp * 4 > 200 * 1024 ? 200 * 1024 : per_warp * 4));
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     const int64_t units = n_seq * heads;
     const int64_t blocks = (units + wpb - 1) / wpb;
-    attn_softmax_kernel<RIP, CJ><<<(unsigned)blocks, 32 * wpb, per_warp * wpb, st>>>(
+    attn_softmax_kernel<RIP, CJ, ALIAS_P><<<(unsigned)blocks, 32 * wpb, per_warp * wpb, st>>>(
         qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride, row_stride,
         rot_cos, rot_sin, pos_bias, wpb);
     LFDM_CHECK_LAUNCH();
@@ -400,9 +402,9 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
     if ((rot_cos == nullptr) != (rot_sin == nullptr)) return LFDM_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
 #define LFDM_ATTN_ARGS qkv, out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride, row_stride, rot_cos, rot_sin, pos_bias, st
-    if (seq_len <= 16) return launch_attn_softmax<4, 2>(LFDM_ATTN_ARGS);
-    if (seq_len <= 40) return launch_attn_softmax<10, 5>(LFDM_ATTN_ARGS);
-    return launch_attn_softmax<8, 8>(LFDM_ATTN_ARGS);        // L <= 64: two row passes of 32
+    if (seq_len <= 16) return launch_attn_softmax<4, 2, true>(LFDM_ATTN_ARGS);
+    if (seq_len <= 40) return launch_attn_softmax<10, 5, true>(LFDM_ATTN_ARGS);
+    return launch_attn_softmax<8, 8, false>(LFDM_ATTN_ARGS);        // L <= 64: two row passes of 32
 #undef LFDM_ATTN_ARGS
 }
 

@@ -141,6 +141,73 @@ __device__ __forceinline__ void epi_chunk16(const TcArgs& a, const uint32_t (&rr
         }
 }
 
+// Coalesced epilogue of a 32-row x 32-column accumulator block of one warp.  The thread-per-row TMEM layout is
+// transposed through a 4 KiB XOR-swizzled smem stage so that 8 consecutive lanes cover one 128-byte row segment:
+// every global store / residual load instruction then touches full 128 B lines (the thread-per-row form issues 32
+// scattered 16 B accesses per instruction).  `orow_l[i]` / `rrow_l[i]` are the output / residual rows of tile row
+// (lane >> 3) + 4 i of this warp's 32-row slab.
+__device__ __forceinline__ void epi_block32(const TcArgs& a, float* stage, const uint32_t (&r0)[16], const uint32_t (&r1)[16],
+                                            int nb, const int32_t (&orow_l)[8], const int32_t (&rrow_l)[8], int bsample,
+                                            int lane) {
+    // ---- write: thread = row `lane`, logical 16-byte chunk q -> physical chunk q ^ (lane & 7)
+    float4* st4 = reinterpret_cast<float4*>(stage) + lane * 8;
+    const int sw = lane & 7;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        st4[q ^ sw] = make_float4(__uint_as_float(r0[4 * q]), __uint_as_float(r0[4 * q + 1]), __uint_as_float(r0[4 * q + 2]),
+                                  __uint_as_float(r0[4 * q + 3]));
+        st4[(q + 4) ^ sw] = make_float4(__uint_as_float(r1[4 * q]), __uint_as_float(r1[4 * q + 1]),
+                                        __uint_as_float(r1[4 * q + 2]), __uint_as_float(r1[4 * q + 3]));
+    }
+    __syncwarp();
+    // ---- read transposed: lane -> (row sub-index lane >> 3, column chunk lane & 7)
+    const int cq = lane & 7, rsub = lane >> 3;
+    const int n = nb + 4 * cq;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias) bias4 = *reinterpret_cast<const float4*>(a.bias + n);
+    float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.out_sb && a.sb_scale) sc4 = *reinterpret_cast<const float4*>(a.sb_scale + n);
+    if (a.out_sb && a.sb_shift) sh4 = *reinterpret_cast<const float4*>(a.sb_shift + n);
+    float gs = 0.f, gq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = rsub + 4 * i;
+        float4 v = reinterpret_cast<const float4*>(stage)[rr * 8 + (cq ^ (rr & 7))];
+        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+        if (a.residual) {
+            const float4 r4 = *reinterpret_cast<const float4*>(a.residual + (int64_t)rrow_l[i] * a.c_out + n);
+            v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+        }
+        if (a.gn_stats) {
+            gs += (v.x + v.y) + (v.z + v.w);
+            gq = fmaf(v.x, v.x, gq); gq = fmaf(v.y, v.y, gq); gq = fmaf(v.z, v.z, gq); gq = fmaf(v.w, v.w, gq);
+        }
+        const int64_t o = (int64_t)orow_l[i] * a.c_out + n;
+        if (a.out_f32)
+            *reinterpret_cast<float4*>(a.out_f32 + o) = make_float4(apply_act(v.x, a.f32_act), apply_act(v.y, a.f32_act),
+                                                                   apply_act(v.z, a.f32_act), apply_act(v.w, a.f32_act));
+        if (a.out_sb)
+            store_sb4(a.out_sb, a.out_plane, o,
+                      make_float4(apply_act(v.x * sc4.x + sh4.x, a.sb_act), apply_act(v.y * sc4.y + sh4.y, a.sb_act),
+                                  apply_act(v.z * sc4.z + sh4.z, a.sb_act), apply_act(v.w * sc4.w + sh4.w, a.sb_act)));
+    }
+    if (a.gn_stats) {
+        // rows: lanes differing in bits 3,4; columns of one group: 4*cq .. -> lanes differing in the low bits
+        gs += __shfl_xor_sync(0xffffffffu, gs, 8);  gq += __shfl_xor_sync(0xffffffffu, gq, 8);
+        gs += __shfl_xor_sync(0xffffffffu, gs, 16); gq += __shfl_xor_sync(0xffffffffu, gq, 16);
+        gs += __shfl_xor_sync(0xffffffffu, gs, 1);  gq += __shfl_xor_sync(0xffffffffu, gq, 1);      // cpg % 8 == 0
+        const int lanes_per_group = a.gn_cpg >= 32 ? 8 : a.gn_cpg / 4;                             // 2, 4 or 8
+        if (lanes_per_group >= 4) { gs += __shfl_xor_sync(0xffffffffu, gs, 2); gq += __shfl_xor_sync(0xffffffffu, gq, 2); }
+        if (lanes_per_group >= 8) { gs += __shfl_xor_sync(0xffffffffu, gs, 4); gq += __shfl_xor_sync(0xffffffffu, gq, 4); }
+        if (rsub == 0 && (cq % lanes_per_group) == 0) {
+            double* stp = a.gn_stats + ((int64_t)bsample * a.gn_groups + n / a.gn_cpg) * 2;
+            atomicAdd(stp, (double)gs);
+            atomicAdd(stp + 1, (double)gq);
+        }
+    }
+    __syncwarp();      // stage is reused by the next block
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
     constexpr int B_BYTES = BN * BK * 2;
@@ -251,6 +318,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int half = (warp - 4) >> 2;    // which column half of the tile this warp drains
         const int r = q * 32 + lane;         // tile row handled by this thread
         const bool vec_ok = (a.c_out % 16) == 0;
+        float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 1024;   // 4 KiB per warp
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
@@ -267,6 +335,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             int64_t rrow = orow;
             if (a.res_bcast_f > 0) rrow = (orow / ((int64_t)a.res_bcast_f * a.p_out)) * a.p_out + (orow % a.p_out);
             const int bsample = a.gn_stats ? (int)(orow / a.rows_per_sample) : 0;
+            // rows this lane handles in the transposed (coalesced) epilogue: tile rows q*32 + (lane>>3) + 4i
+            int32_t orow_l[8], rrow_l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int src_lane = (lane >> 3) + 4 * i;
+                const int64_t oo = __shfl_sync(0xffffffffu, orow, src_lane);
+                const int64_t rro = __shfl_sync(0xffffffffu, rrow, src_lane);
+                orow_l[i] = (int32_t)oo; rrow_l[i] = (int32_t)rro;
+            }
 
             ptx::mbar_wait(&tfull_bar[as], aphase);
             ptx::tc_fence_after();
@@ -282,8 +359,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         ptx::tmem_ld16(taddr + col0 + c0, r0);
                         ptx::tmem_ld16(taddr + col0 + c0 + 16, r1);
                         ptx::tmem_ld_wait();
-                        epi_chunk16(a, r0, n0 + col0 + c0, orow, rrow, bsample, lane, vec_ok);
-                        epi_chunk16(a, r1, n0 + col0 + c0 + 16, orow, rrow, bsample, lane, vec_ok);
+                        if (vec_ok && (n0 + col0 + c0 + 32 <= a.c_out)) {
+                            epi_block32(a, stage, r0, r1, n0 + col0 + c0, orow_l, rrow_l, bsample, lane);
+                        } else {
+                            epi_chunk16(a, r0, n0 + col0 + c0, orow, rrow, bsample, lane, vec_ok);
+                            epi_chunk16(a, r1, n0 + col0 + c0 + 16, orow, rrow, bsample, lane, vec_ok);
+                        }
                     }
                 } else {
                     uint32_t r0[16];
@@ -340,7 +421,7 @@ int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims
 template <int BN, int STAGES>
 int launch(const TcArgs& a, cudaStream_t st) {
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BN * BK * 2;
-    constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 4096;   // + barriers + 8 epilogue staging tiles
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);

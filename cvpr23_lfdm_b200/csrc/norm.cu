@@ -83,47 +83,69 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     }
 }
 
-// ---------------- LayerNorm over channels: one warp per row; c % 4 == 0, c <= 1024
+// ---------------- LayerNorm over channels: c % 4 == 0, c <= 1024.  A row is handled by G = c4-rounded-up-to-pow2
+// (<= 32) lanes or by a full warp with NJ float4 per lane; R rows are in flight per warp iteration so that a warp
+// always has >= 8 independent 16-byte loads outstanding (the kernel is pure HBM streaming).
+template <int G, int NJ>      // G lanes per row (G <= 32), NJ float4 per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         bf16* __restrict__ out_sb, int64_t out_plane,
                                                         float* __restrict__ out_f32, int64_t m, int c, float eps) {
+    constexpr int RPW = 32 / G;                 // rows per warp per pass
+    constexpr int PASSES = (NJ >= 4) ? 1 : (4 / NJ);   // independent row passes kept in flight
     const int lane = threadIdx.x & 31;
+    const int sub = lane / G, gl = lane % G;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int c4 = c >> 2;
-    for (int64_t row = warp; row < m; row += nwarps) {
-        float4 v[8];
-        float s = 0.f;
+    float4 g[NJ];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            int q = lane + 32 * j;
-            if (q < c4) {
-                v[j] = *reinterpret_cast<const float4*>(x + row * c + q * 4);
-                s += v[j].x + v[j].y + v[j].z + v[j].w;
+    for (int j = 0; j < NJ; ++j) {
+        const int q = gl + G * j;
+        g[j] = q < c4 ? *reinterpret_cast<const float4*>(gamma + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int64_t row0 = warp * (RPW * PASSES); row0 < m; row0 += nwarps * (RPW * PASSES)) {
+        float4 v[PASSES][NJ];
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const int64_t row = row0 + p * RPW + sub;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int q = gl + G * j;
+                v[p][j] = (row < m && q < c4) ? *reinterpret_cast<const float4*>(x + row * c + q * 4)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        s = warp_sum(s);
-        float mean = s / (float)c;
-        float sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            int q = lane + 32 * j;
-            if (q < c4) {
-                float a = v[j].x - mean, b = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
-                sq += a * a + b * b + cc * cc + d * d;
+        for (int p = 0; p < PASSES; ++p) {
+            const int64_t row = row0 + p * RPW + sub;
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) s += (v[p][j].x + v[p][j].y) + (v[p][j].z + v[p][j].w);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s / (float)c;
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (gl + G * j < c4) {
+                    const float a = v[p][j].x - mean, b = v[p][j].y - mean, cc = v[p][j].z - mean, d = v[p][j].w - mean;
+                    sq += a * a + b * b + cc * cc + d * d;
+                }
             }
-        }
-        sq = warp_sum(sq);
-        float rstd = 1.f / sqrtf(sq / (float)c + eps);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            int q = lane + 32 * j;
-            if (q < c4) {
-                float4 g = *reinterpret_cast<const float4*>(gamma + q * 4);
-                float4 o = make_float4((v[j].x - mean) * rstd * g.x, (v[j].y - mean) * rstd * g.y,
-                                       (v[j].z - mean) * rstd * g.z, (v[j].w - mean) * rstd * g.w);
-                if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * c + q * 4) = o;
-                if (out_sb) store_sb4(out_sb, out_plane, row * c + q * 4, o);
+            for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const float rstd = 1.f / sqrtf(sq / (float)c + eps);
+            if (row < m) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int q = gl + G * j;
+                    if (q < c4) {
+                        const float4 o4 = make_float4((v[p][j].x - mean) * rstd * g[j].x, (v[p][j].y - mean) * rstd * g[j].y,
+                                                      (v[p][j].z - mean) * rstd * g[j].z, (v[p][j].w - mean) * rstd * g[j].w);
+                        if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * c + q * 4) = o4;
+                        if (out_sb) store_sb4(out_sb, out_plane, row * c + q * 4, o4);
+                    }
+                }
             }
         }
     }
@@ -167,9 +189,24 @@ extern "C" int lfdm_gn_apply(const float* x, const double* stats, const float* g
 extern "C" int lfdm_layernorm(const float* x, const float* gamma, void* out_sb, int64_t out_plane, float* out_f32,
                               int64_t m, int c, float eps, void* stream) {
     if (!x || !gamma || (c & 3) || c > 1024) return LFDM_E_BADARG;
-    int64_t blocks = (m + 7) / 8;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    layernorm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, (bf16*)out_sb, out_plane, out_f32, m, c, eps);
+    const int c4 = c >> 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t rows_per_block;
+#define LFDM_LN_LAUNCH(G, NJ)                                                                                         \
+    do {                                                                                                              \
+        rows_per_block = 8 * (32 / G) * ((NJ >= 4) ? 1 : (4 / NJ));                                                   \
+        int64_t blocks = (m + rows_per_block - 1) / rows_per_block;                                                   \
+        if (blocks > 148 * 16) blocks = 148 * 16;                                                                     \
+        layernorm_kernel<G, NJ><<<(int)blocks, 256, 0, st>>>(x, gamma, (bf16*)out_sb, out_plane, out_f32, m, c, eps);  \
+    } while (0)
+    if (c4 <= 4) LFDM_LN_LAUNCH(4, 1);
+    else if (c4 <= 8) LFDM_LN_LAUNCH(8, 1);
+    else if (c4 <= 16) LFDM_LN_LAUNCH(16, 1);
+    else if (c4 <= 32) LFDM_LN_LAUNCH(32, 1);
+    else if (c4 <= 64) LFDM_LN_LAUNCH(32, 2);
+    else if (c4 <= 128) LFDM_LN_LAUNCH(32, 4);
+    else LFDM_LN_LAUNCH(32, 8);
+#undef LFDM_LN_LAUNCH
     LFDM_CHECK_LAUNCH();
     return 0;
 }

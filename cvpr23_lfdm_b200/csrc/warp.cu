@@ -80,13 +80,28 @@ __global__ void __launch_bounds__(256) warp_rows_kernel(const float* __restrict_
                                                         const float* __restrict__ sb_shift, int sb_act, int64_t n_img,
                                                         int frames_per_src, int hs, int ws, int c, int hf, int wf) {
     const int c4 = c >> 2;
+    const bool tiled = ((hs | ws) & 3) == 0;
     const int64_t total = n_img * hs * ws * c4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int cq = (int)(i % c4);
-        const int64_t pix = i / c4;
-        const int x = (int)(pix % ws);
-        const int y = (int)((pix / ws) % hs);
-        const int64_t n = pix / ((int64_t)hs * ws);
+        int64_t pix = i / c4;
+        int x, y;
+        int64_t n;
+        if (tiled) {
+            // walk 4x4 pixel patches: neighbouring threads sample neighbouring source texels -> the 4 bilinear taps
+            // of a patch hit in L1 instead of going back to L2 for every output pixel
+            const int t = (int)(pix & 15);
+            const int64_t tile = pix >> 4;
+            const int tw = ws >> 2, th = hs >> 2;
+            x = (int)(tile % tw) * 4 + (t & 3);
+            y = (int)((tile / tw) % th) * 4 + (t >> 2);
+            n = tile / ((int64_t)tw * th);
+            pix = (n * hs + y) * ws + x;
+        } else {
+            x = (int)(pix % ws);
+            y = (int)((pix / ws) % hs);
+            n = pix / ((int64_t)hs * ws);
+        }
         float gx, gy, oc;
         latent_at(flow, occ, n, y, x, hs, ws, hf, wf, gx, gy, oc);
         const Taps t = make_taps(gx, gy, hs, ws);
