@@ -99,22 +99,49 @@ def install_shims(patch_cuda=None):
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.nn.Module._lfdm_cuda_patched = True
 
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+
+
+_NS = None
+_REF_TOP = ("DM", "LFAE", "misc", "sync_batchnorm")
 
 
 def import_reference():
-    """Returns a namespace with the reference's hot-path classes."""
+    """Returns a namespace with the reference's hot-path classes, imported from REFERENCE_ROOT.
+
+    This repo ships alias packages with the reference's own top-level names (`DM`, `LFAE`, `misc`: the drop-in import
+    path of INTEGRATION.md), so the reference is imported with those names temporarily unbound and its modules are
+    then detached from `sys.modules` again — both implementations can live in one process without shadowing."""
+    global _NS
+    if _NS is not None:
+        return _NS
     install_shims()
+    stash = {k: v for k, v in sys.modules.items() if k.split(".")[0] in _REF_TOP}
+    for k in stash:
+        del sys.modules[k]
+    # the reference's DM/ and LFAE/ are namespace packages (no __init__.py): a regular package of the same name
+    # anywhere on sys.path would win, so every path entry that holds one is hidden during the import
+    saved_path = list(sys.path)
+    sys.path[:] = [REFERENCE_ROOT] + [p_ for p_ in saved_path if p_ != REFERENCE_ROOT and not any(
+        os.path.exists(os.path.join(p_ or ".", t, "__init__.py")) or os.path.exists(os.path.join(p_ or ".", t + ".py"))
+        for t in _REF_TOP)]
     ns = types.SimpleNamespace()
-    import DM.modules.video_flow_diffusion as vfd
-    import DM.modules.video_flow_diffusion_model as vfdm
-    import LFAE.modules.generator as gen
-    import LFAE.modules.region_predictor as rp
-    import LFAE.modules.bg_motion_predictor as bg
-    import LFAE.modules.util as util
+    try:
+        import DM.modules.video_flow_diffusion as vfd
+        import DM.modules.video_flow_diffusion_model as vfdm
+        import LFAE.modules.generator as gen
+        import LFAE.modules.region_predictor as rp
+        import LFAE.modules.bg_motion_predictor as bg
+        import LFAE.modules.util as util
+        for m in (vfd, vfdm, gen, rp, bg, util):
+            assert os.path.abspath(m.__file__).startswith(os.path.abspath(REFERENCE_ROOT)), m.__file__
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k.split(".")[0] in _REF_TOP]:
+            del sys.modules[k]
+        sys.modules.update(stash)
     ns.vfd, ns.vfdm, ns.gen, ns.rp, ns.bg, ns.util = vfd, vfdm, gen, rp, bg, util
     ns.Unet3D, ns.GaussianDiffusion = vfd.Unet3D, vfd.GaussianDiffusion
     ns.FlowDiffusion = vfdm.FlowDiffusion
     ns.Generator, ns.RegionPredictor, ns.BGMotionPredictor = gen.Generator, rp.RegionPredictor, bg.BGMotionPredictor
+    _NS = ns
     return ns
