@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
     extern __shared__ __align__(16) float s_dynl[];      // [LW][2 stages][2 tiles][32][TP]; aliased by the reduction
     __shared__ float s_red[LW][DH];
     __shared__ float s_max[DH];
-    __shared__ __align__(16) float s_ctxn[DH][DH + 4];
+    float (*s_ctxn)[DH + 4] = reinterpret_cast<float (*)[DH + 4]>(s_dynl + LW * DH * DH);   // aliases tiles (after phase 2)
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a = lane >> 3, b = lane & 7;
     const int64_t fr = blockIdx.x / heads;
@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
         const float4 t = *reinterpret_cast<const float4*>(&s_ctxn[8 * a + i][4 * b]);
         ctx[i][0] = t.x; ctx[i][1] = t.y; ctx[i][2] = t.z; ctx[i][3] = t.w;
     }
+    __syncthreads();                                     // s_ctxn (aliased) fully consumed before q tiles land on it
 
     // phase 3: out[n][e] = sum_d ctxn[d][e] * softmax_d(q[n])[d] * scale
     if (w < n_chunks) issue_rows(wbuf, base, ld, w * 32, n_pos, lane);

@@ -73,68 +73,89 @@ __device__ __forceinline__ float4 fma4(float4 acc, float4 v, float w) {
     return acc;
 }
 
+// One warp owns 32 consecutive output pixels.  Phase 1: lane p computes the per-pixel set-up ONCE (up-sampled flow and
+// occlusion, 4 tap offsets + weights) — per pixel, not per float4 as a naive mapping would.  Phase 2: the warp walks the
+// pixels, broadcasting a pixel's set-up with shuffles while the lanes sweep its channels with 16-byte accesses, so
+// every load/store instruction covers contiguous 128..512 B runs of the channels-last rows.
 __global__ void __launch_bounds__(256) warp_rows_kernel(const float* __restrict__ src, const float* __restrict__ flow,
                                                         const float* __restrict__ occ, const float* __restrict__ prev,
                                                         float* __restrict__ out_f32, bf16* __restrict__ out_sb,
                                                         int64_t out_plane, const float* __restrict__ sb_scale,
                                                         const float* __restrict__ sb_shift, int sb_act, int64_t n_img,
                                                         int frames_per_src, int hs, int ws, int c, int hf, int wf) {
-    const int c4 = c >> 2;
-    const bool tiled = ((hs | ws) & 3) == 0;
-    const int64_t total = n_img * hs * ws * c4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cq = (int)(i % c4);
-        int64_t pix = i / c4;
-        int x, y;
-        int64_t n;
-        if (tiled) {
-            // walk 4x4 pixel patches: neighbouring threads sample neighbouring source texels -> the 4 bilinear taps
-            // of a patch hit in L1 instead of going back to L2 for every output pixel
-            const int t = (int)(pix & 15);
-            const int64_t tile = pix >> 4;
-            const int tw = ws >> 2, th = hs >> 2;
-            x = (int)(tile % tw) * 4 + (t & 3);
-            y = (int)((tile / tw) % th) * 4 + (t >> 2);
-            n = tile / ((int64_t)tw * th);
-            pix = (n * hs + y) * ws + x;
-        } else {
-            x = (int)(pix % ws);
-            y = (int)((pix / ws) % hs);
-            n = pix / ((int64_t)hs * ws);
+    const int lane = threadIdx.x & 31;
+    const int qpp = c >> 2;                                  // float4 per pixel
+    int lpp = 1;                                             // lanes per pixel: largest power of two <= min(32, qpp)
+    while (lpp * 2 <= qpp && lpp < 32) lpp *= 2;
+    const int ppi = 32 / lpp;                                // pixels per iteration
+    const int64_t total_pix = n_img * hs * ws;
+    const int64_t n_groups = (total_pix + 31) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int hw = hs * ws;
+    for (int64_t g = warp0; g < n_groups; g += nwarps) {
+        // ---- phase 1: per-pixel set-up (lane = pixel)
+        const int64_t pix = (g << 5) + lane;
+        int off[4] = {-1, -1, -1, -1};
+        float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+        float oc = 1.f;
+        if (pix < total_pix) {
+            const int n = (int)(pix / hw);
+            const int rem = (int)(pix - (int64_t)n * hw);
+            const int y = rem / ws, x = rem - y * ws;
+            float gx, gy;
+            latent_at(flow, occ, n, y, x, hs, ws, hf, wf, gx, gy, oc);
+            const Taps t = make_taps(gx, gy, hs, ws);
+            const int sbase = (n / frames_per_src) * hw;     // source image row offset (in pixels)
+            if (t.vy0 && t.vx0) off[0] = sbase + t.y0 * ws + t.x0;
+            if (t.vy0 && t.vx1) off[1] = sbase + t.y0 * ws + t.x1;
+            if (t.vy1 && t.vx0) off[2] = sbase + t.y1 * ws + t.x0;
+            if (t.vy1 && t.vx1) off[3] = sbase + t.y1 * ws + t.x1;
+            wgt[0] = t.wnw; wgt[1] = t.wne; wgt[2] = t.wsw; wgt[3] = t.wse;
         }
-        float gx, gy, oc;
-        latent_at(flow, occ, n, y, x, hs, ws, hf, wf, gx, gy, oc);
-        const Taps t = make_taps(gx, gy, hs, ws);
-        const float* sb = src + (n / frames_per_src) * (int64_t)hs * ws * c + cq * 4;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t.vy0 && t.vx0) acc = fma4(acc, *reinterpret_cast<const float4*>(sb + ((int64_t)t.y0 * ws + t.x0) * c), t.wnw);
-        if (t.vy0 && t.vx1) acc = fma4(acc, *reinterpret_cast<const float4*>(sb + ((int64_t)t.y0 * ws + t.x1) * c), t.wne);
-        if (t.vy1 && t.vx0) acc = fma4(acc, *reinterpret_cast<const float4*>(sb + ((int64_t)t.y1 * ws + t.x0) * c), t.wsw);
-        if (t.vy1 && t.vx1) acc = fma4(acc, *reinterpret_cast<const float4*>(sb + ((int64_t)t.y1 * ws + t.x1) * c), t.wse);
-        const int64_t o = pix * c + cq * 4;
-        float4 r;
-        if (occ) {
-            r = make_float4(acc.x * oc, acc.y * oc, acc.z * oc, acc.w * oc);
-            if (prev) {
-                const float4 p = *reinterpret_cast<const float4*>(prev + o);
-                const float om = 1.f - oc;
-                r.x += p.x * om; r.y += p.y * om; r.z += p.z * om; r.w += p.w * om;
-            }
-        } else {
-            r = acc;
-        }
-        if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = r;
-        if (out_sb) {
-            float u[4] = {r.x, r.y, r.z, r.w};
+        // ---- phase 2: sweep channels
+        const int sub = lane / lpp, ql = lane - sub * lpp;
+        for (int it = 0; it < 32; it += ppi) {
+            const int pl = it + sub;                          // pixel (lane index) this lane works on
+            const int o0 = __shfl_sync(0xffffffffu, off[0], pl), o1 = __shfl_sync(0xffffffffu, off[1], pl);
+            const int o2 = __shfl_sync(0xffffffffu, off[2], pl), o3 = __shfl_sync(0xffffffffu, off[3], pl);
+            const float w0 = __shfl_sync(0xffffffffu, wgt[0], pl), w1 = __shfl_sync(0xffffffffu, wgt[1], pl);
+            const float w2 = __shfl_sync(0xffffffffu, wgt[2], pl), w3 = __shfl_sync(0xffffffffu, wgt[3], pl);
+            const float ocp = __shfl_sync(0xffffffffu, oc, pl);
+            const int64_t p = (g << 5) + pl;
+            if (p >= total_pix) continue;                     // uniform per sub-group; shuffles above are done by all
+            for (int q = ql; q < qpp; q += lpp) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (o0 >= 0) acc = fma4(acc, *reinterpret_cast<const float4*>(src + (int64_t)o0 * c + q * 4), w0);
+                if (o1 >= 0) acc = fma4(acc, *reinterpret_cast<const float4*>(src + (int64_t)o1 * c + q * 4), w1);
+                if (o2 >= 0) acc = fma4(acc, *reinterpret_cast<const float4*>(src + (int64_t)o2 * c + q * 4), w2);
+                if (o3 >= 0) acc = fma4(acc, *reinterpret_cast<const float4*>(src + (int64_t)o3 * c + q * 4), w3);
+                const int64_t o = p * c + q * 4;
+                float4 r;
+                if (occ) {
+                    r = make_float4(acc.x * ocp, acc.y * ocp, acc.z * ocp, acc.w * ocp);
+                    if (prev) {
+                        const float4 pv = *reinterpret_cast<const float4*>(prev + o);
+                        const float om = 1.f - ocp;
+                        r.x += pv.x * om; r.y += pv.y * om; r.z += pv.z * om; r.w += pv.w * om;
+                    }
+                } else {
+                    r = acc;
+                }
+                if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = r;
+                if (out_sb) {
+                    float u[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                int cc = cq * 4 + e;
-                float v = u[e];
-                if (sb_scale) v *= sb_scale[cc];
-                if (sb_shift) v += sb_shift[cc];
-                u[e] = apply_act(v, sb_act);
+                    for (int e = 0; e < 4; ++e) {
+                        const int cc = q * 4 + e;
+                        float v = u[e];
+                        if (sb_scale) v *= sb_scale[cc];
+                        if (sb_shift) v += sb_shift[cc];
+                        u[e] = apply_act(v, sb_act);
+                    }
+                    store_sb4(out_sb, out_plane, o, make_float4(u[0], u[1], u[2], u[3]));
+                }
             }
-            store_sb4(out_sb, out_plane, o, make_float4(u[0], u[1], u[2], u[3]));
         }
     }
 }
@@ -179,9 +200,10 @@ extern "C" int lfdm_warp_blend_rows(const float* src, const float* flow, const f
                                     const float* sb_shift, int sb_act, int n, int frames_per_src, int hs, int ws, int c,
                                     int hf, int wf, void* stream) {
     if (!src || !flow || (c & 3) || frames_per_src <= 0 || (!out_f32 && !out_sb)) return LFDM_E_BADARG;
-    int64_t total = (int64_t)n * hs * ws * (c >> 2);
-    int64_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    int64_t groups = ((int64_t)n * hs * ws + 31) / 32;
+    int64_t blocks = (groups + 7) / 8;                  // 8 warps per block, one 32-pixel group per warp iteration
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if ((int64_t)n * hs * ws >= (1ll << 31) / 1 || (int64_t)(n / frames_per_src + 1) * hs * ws >= (1ll << 31)) return LFDM_E_BADARG;
     warp_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, flow, occ, prev, out_f32, (bf16*)out_sb,
                                                                         out_plane, sb_scale, sb_shift, sb_act, n,
                                                                         frames_per_src, hs, ws, c, hf, wf);

@@ -245,6 +245,24 @@ def test_attn_temporal_and_spatial():
     close(out, ref_s, "spatial attention")
 
 
+@pytest.mark.parametrize("L", [5, 24, 40, 49, 64])
+def test_attn_softmax_lengths(L):
+    """every register-tile configuration of the softmax attention core (L <= 16, <= 40, <= 64 with two row passes)"""
+    from cvpr23_lfdm_b200.engine import ops
+    g = torch.Generator().manual_seed(30 + L)
+    n_seq, heads = 5, 3
+    hid = heads * 32
+    qkv = torch.randn(n_seq, L, 3 * hid, generator=g)
+    q, k, v = [t.reshape(n_seq, L, heads, 32).transpose(1, 2) for t in qkv.chunk(3, -1)]
+    sim = torch.einsum("shid,shjd->shij", q * 32 ** -0.5, k)
+    att = (sim - sim.amax(-1, keepdim=True)).softmax(-1)
+    ref = torch.einsum("shij,shjd->shid", att, v).transpose(1, 2).reshape(n_seq * L, hid)
+    out = torch.empty(n_seq * L, hid, device=dev())
+    qd = qkv.reshape(n_seq * L, 3 * hid).to(dev())
+    ops.attn_softmax(qd, None, out, n_seq, L, heads, 1, L, 0, 1)
+    close(out, ref, f"softmax attention L={L}")
+
+
 @pytest.mark.parametrize("n_pos", [16, 64, 1024])
 def test_attn_linear(n_pos):
     from cvpr23_lfdm_b200.engine import ops

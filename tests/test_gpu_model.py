@@ -219,3 +219,33 @@ def test_tiny_generator_forward_and_predictors_match_reference_golden(golden):
     bg.load_state_dict(g["bg_sd"])
     bg = bg.cuda().eval()
     close(bg(g["img"].cuda(), g["drv"].cuda()), g["bg"], "BGMotionPredictor")
+
+
+# ------------------------------------------------------------------------------------------------ other configs
+def test_natops_style_unet_vs_oracle():
+    """NATOPS constructor options (demo_natops.py:23-32): nearest-upsample + reflect-padded conv, learned null cond, CFG"""
+    import cvpr23_lfdm_b200 as P
+    from oracle import lfdm_oracle as O
+    torch.manual_seed(31)
+    u = P.Unet3D(dim=16, cond_dim=24, dim_mults=(1, 2, 4), channels=11, attn_heads=2, use_deconv=False,
+                 padding_mode="reflect", learn_null_cond=True)
+    sd = {k: v.detach().clone() for k, v in u.state_dict().items()}
+    u = u.cuda().eval()
+    x, t, c = torch.randn(2, 11, 6, 16, 16), torch.tensor([900, 3]), torch.randn(2, 24)
+    for cs in (1.0, 2.5):
+        ref = O.unet3d_forward_with_cond_scale(sd, x, t, c, cs, heads=2, padding_mode="reflect")
+        got = u.forward_with_cond_scale(x.cuda(), t.cuda(), cond=c.cuda(), cond_scale=cs)
+        close(got, ref, f"natops-style unet cond_scale={cs}", rtol=2e-3, atol=2e-4)
+
+
+def test_full_unet_256res_geometry_vs_oracle(full_model):
+    """MUG-256 geometry (latent 64x64: 64-wide tiles, 64-token mid attention) on the full-size UNet, 8 frames"""
+    from oracle import lfdm_oracle as O
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(1, 259, 8, 64, 64, generator=g)
+    t = torch.tensor([123])
+    cond = torch.randn(1, 768, generator=g)
+    sd = {k: v.detach().cpu() for k, v in full_model.unet.state_dict().items()}
+    ref = O.unet3d_forward(sd, x, t, cond)
+    got = full_model.unet(x.cuda(), t.cuda(), cond=cond.cuda())
+    close(got, ref, "full UNet @ 64x64 latent")
