@@ -58,6 +58,9 @@ def conv_case(cin, cout, hw, k, gn=False, residual=False, srcs=1):
 def cases():
     c = {}
     c["conv3x3_c64_32"] = lambda: conv_case(64, 64, 32, 3, gn=True)
+    c["conv3x3_c64_32_nogn"] = lambda: conv_case(64, 64, 32, 3, gn=False)
+    c["conv1x1_c64_32_nogn"] = lambda: conv_case(64, 64, 32, 1, gn=False)
+    c["conv3x3_c256_32_nogn"] = lambda: conv_case(256, 256, 32, 3, gn=False)
     c["conv3x3_c64x2_32"] = lambda: conv_case(64, 64, 32, 3, gn=True, srcs=2)
     c["conv3x3_c128_16"] = lambda: conv_case(128, 128, 16, 3, gn=True)
     c["conv3x3_c256_8"] = lambda: conv_case(256, 256, 8, 3, gn=True)
