@@ -100,16 +100,25 @@ __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restri
         for (int r = 0; r < RIP; ++r)
 #pragma unroll
             for (int c = 0; c < CJ; ++c) acc[r][c] = 0.f;
-#pragma unroll 2
+        // rows i0 + a + 4r never exceed LP - 1 when the pass covers exactly 4*RIP rows of an LP-row tile
+        constexpr bool ROWS_IN_RANGE = (CJ * 8) % (4 * RIP) == 0;
+        const float* sq_a = sq + (i0 + a) * QP;
+        const float* sk_b = sk + b * QP;
+#pragma unroll
         for (int d = 0; d < DH; d += 4) {
             float4 kq[CJ];
 #pragma unroll
-            for (int c = 0; c < CJ; ++c) kq[c] = *reinterpret_cast<const float4*>(sk + (b + 8 * c) * QP + d);
+            for (int c = 0; c < CJ; ++c) kq[c] = *reinterpret_cast<const float4*>(sk_b + 8 * c * QP + d);
 #pragma unroll
             for (int r = 0; r < RIP; ++r) {
-                int i = i0 + a + 4 * r;
-                i = i < LP ? i : LP - 1;
-                const float4 qv = *reinterpret_cast<const float4*>(sq + i * QP + d);
+                float4 qv;
+                if (ROWS_IN_RANGE) {
+                    qv = *reinterpret_cast<const float4*>(sq_a + 4 * r * QP + d);
+                } else {
+                    int i = i0 + a + 4 * r;
+                    i = i < LP ? i : LP - 1;
+                    qv = *reinterpret_cast<const float4*>(sq + i * QP + d);
+                }
 #pragma unroll
                 for (int c = 0; c < CJ; ++c) {
                     acc[r][c] = fmaf(qv.x, kq[c].x, acc[r][c]);
@@ -159,16 +168,24 @@ __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restri
         float4 o[RIP];
 #pragma unroll
         for (int r = 0; r < RIP; ++r) o[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* sp_a = sp + (i0 + a) * PP;
+        const float* sv_b = sv + 4 * b;
+#pragma unroll
         for (int j = 0; j < LP; j += 4) {
-            const float4 v0 = *reinterpret_cast<const float4*>(sv + (j + 0) * QP + 4 * b);
-            const float4 v1 = *reinterpret_cast<const float4*>(sv + (j + 1) * QP + 4 * b);
-            const float4 v2 = *reinterpret_cast<const float4*>(sv + (j + 2) * QP + 4 * b);
-            const float4 v3 = *reinterpret_cast<const float4*>(sv + (j + 3) * QP + 4 * b);
+            const float4 v0 = *reinterpret_cast<const float4*>(sv_b + (j + 0) * QP);
+            const float4 v1 = *reinterpret_cast<const float4*>(sv_b + (j + 1) * QP);
+            const float4 v2 = *reinterpret_cast<const float4*>(sv_b + (j + 2) * QP);
+            const float4 v3 = *reinterpret_cast<const float4*>(sv_b + (j + 3) * QP);
 #pragma unroll
             for (int r = 0; r < RIP; ++r) {
-                int i = i0 + a + 4 * r;
-                i = i < LP ? i : LP - 1;
-                const float4 p = *reinterpret_cast<const float4*>(sp + i * PP + j);
+                float4 p;
+                if (ROWS_IN_RANGE) {
+                    p = *reinterpret_cast<const float4*>(sp_a + 4 * r * PP + j);
+                } else {
+                    int i = i0 + a + 4 * r;
+                    i = i < LP ? i : LP - 1;
+                    p = *reinterpret_cast<const float4*>(sp + i * PP + j);
+                }
                 o[r].x = fmaf(p.x, v0.x, o[r].x); o[r].y = fmaf(p.x, v0.y, o[r].y); o[r].z = fmaf(p.x, v0.z, o[r].z); o[r].w = fmaf(p.x, v0.w, o[r].w);
                 o[r].x = fmaf(p.y, v1.x, o[r].x); o[r].y = fmaf(p.y, v1.y, o[r].y); o[r].z = fmaf(p.y, v1.z, o[r].z); o[r].w = fmaf(p.y, v1.w, o[r].w);
                 o[r].x = fmaf(p.z, v2.x, o[r].x); o[r].y = fmaf(p.z, v2.y, o[r].y); o[r].z = fmaf(p.z, v2.z, o[r].z); o[r].w = fmaf(p.z, v2.w, o[r].w);

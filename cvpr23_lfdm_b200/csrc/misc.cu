@@ -107,27 +107,36 @@ __global__ void __launch_bounds__(256) from_rows_kernel(const float* __restrict_
     }
 }
 
-// in[b][c][f][h][w] -> SB rows [M][k_pad], k = (kh*ks + kw)*c + ch, zero padded borders / k >= ks*ks*c
+// in[b][c][f][h][w] -> SB rows [M][k_pad], k = (kh*ks + kw)*c + ch, zero padded borders / k >= ks*ks*c.
+// One thread produces 4 consecutive k of one row (8-byte stores into each plane); 32-bit index math.
 __global__ void __launch_bounds__(256) im2col_small_kernel(const float* __restrict__ in, int c, int f, int h, int w,
                                                            int ks, int pad, int k_pad, bf16* __restrict__ out_sb,
-                                                           int64_t out_plane, int64_t total) {
+                                                           int64_t out_plane, int64_t total4) {
     const int kreal = ks * ks * c;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int k = (int)(i % k_pad);
-        int64_t m = i / k_pad;
-        float v = 0.f;
-        if (k < kreal) {
-            int tap = k / c, ch = k - tap * c;
-            int kh = tap / ks, kw = tap - kh * ks;
-            int x = (int)(m % w);
-            int y = (int)((m / w) % h);
-            int64_t n = m / ((int64_t)h * w);
-            int bi = (int)(n / f), fi = (int)(n % f);
-            int yy = y - pad + kh, xx = x - pad + kw;
-            if (yy >= 0 && yy < h && xx >= 0 && xx < w)
-                v = in[((((int64_t)bi * c + ch) * f + fi) * h + yy) * w + xx];
+    const int kq_per_row = k_pad >> 2;
+    const int hw = h * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / kq_per_row);
+        const int kq = (int)(i - (int64_t)m * kq_per_row);
+        const int n = m / hw;
+        const int rem = m - n * hw;
+        const int y = rem / w, x = rem - y * w;
+        const int bi = n / f, fi = n - bi * f;
+        const float* base = in + ((int64_t)bi * c * f + fi) * hw;           // + ch * f * hw + yy * w + xx
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = kq * 4 + e;
+            float val = 0.f;
+            if (k < kreal) {
+                const int tap = k / c, ch = k - tap * c;
+                const int kh = tap / ks, kw = tap - kh * ks;
+                const int yy = y - pad + kh, xx = x - pad + kw;
+                if (yy >= 0 && yy < h && xx >= 0 && xx < w) val = base[(int64_t)ch * f * hw + yy * w + xx];
+            }
+            v[e] = val;
         }
-        store_sb1(out_sb, out_plane, i, v);
+        store_sb4(out_sb, out_plane, (int64_t)m * k_pad + kq * 4, make_float4(v[0], v[1], v[2], v[3]));
     }
 }
 
@@ -243,10 +252,11 @@ extern "C" int lfdm_from_rows(const float* rows, int ld, int b, int c, int f, in
 
 extern "C" int lfdm_im2col_small(const float* in, int b, int c, int f, int h, int w, int ksize, int pad, int k_pad,
                                  void* out_sb, int64_t out_plane, void* stream) {
-    if (!in || !out_sb || k_pad < ksize * ksize * c) return LFDM_E_BADARG;
-    int64_t total = (int64_t)b * f * h * w * k_pad;
-    im2col_small_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, c, f, h, w, ksize, pad, k_pad,
-                                                                        (bf16*)out_sb, out_plane, total);
+    if (!in || !out_sb || k_pad < ksize * ksize * c || (k_pad & 3)) return LFDM_E_BADARG;
+    if ((int64_t)b * f * h * w >= (1ll << 31)) return LFDM_E_BADARG;
+    int64_t total4 = (int64_t)b * f * h * w * (k_pad >> 2);
+    im2col_small_kernel<<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(in, c, f, h, w, ksize, pad, k_pad,
+                                                                         (bf16*)out_sb, out_plane, total4);
     LFDM_CHECK_LAUNCH();
     return 0;
 }
