@@ -212,7 +212,9 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    constexpr int ACC = 4;                      // TMEM accumulator ring depth (4 x BN <= 512 columns)
+    constexpr uint32_t TMEM_COLS = (ACC * BN <= 32) ? 32 : (ACC * BN <= 64) ? 64 : (ACC * BN <= 128) ? 128 : (ACC * BN <= 256) ? 256 : 512;
+    static_assert(ACC * BN <= 512, "accumulator ring exceeds TMEM");
     constexpr uint32_t IDESC = ptx::make_idesc_bf16(BM, BN);
 
     extern __shared__ uint8_t smem_raw[];
@@ -220,8 +222,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* tempty_bar = tfull_bar + ACC;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + ACC);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     if (warp == 1 && ptx::elect_one()) {
         for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], NUM_THREADS - 128); }
+        for (int i = 0; i < ACC; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 128); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -284,8 +286,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         int stage = 0; uint32_t phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
+            const int as = it % ACC;
+            const uint32_t aphase = (it / ACC) & 1;
             ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * BN;
@@ -315,14 +317,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;              // TMEM lane quarter this warp may access (warp % 4)
-        const int half = (warp - 4) >> 2;    // which column half of the tile this warp drains
+        const int grp = (warp - 4) >> 2;     // two epilogue groups of 4 warps drain alternate tiles concurrently
         const int r = q * 32 + lane;         // tile row handled by this thread
         const bool vec_ok = (a.c_out % 16) == 0;
         float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 1024;   // 4 KiB per warp
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
+        for (int it = grp;; it += 2) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            if (tile >= total_tiles) break;
+            const int as = it % ACC;
+            const uint32_t aphase = (it / ACC) & 1;
             const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
             const int w_t = m_tile % a.tiles_w;
             const int h_t = (m_tile / a.tiles_w) % a.tiles_h;
@@ -348,30 +351,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             ptx::mbar_wait(&tfull_bar[as], aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            constexpr int EPI_SPLIT = (BN >= 32) ? 2 : 1;          // column halves handled by warps 4-7 / 8-11
-            constexpr int WCOLS = BN / EPI_SPLIT;
-            const int col0 = (EPI_SPLIT == 2) ? half * WCOLS : 0;
-            if (EPI_SPLIT == 2 || half == 0) {
-                if constexpr (WCOLS >= 32) {
+            if constexpr (BN >= 32) {
 #pragma unroll 1
-                    for (int c0 = 0; c0 < WCOLS; c0 += 32) {
-                        uint32_t r0[16], r1[16];
-                        ptx::tmem_ld16(taddr + col0 + c0, r0);
-                        ptx::tmem_ld16(taddr + col0 + c0 + 16, r1);
-                        ptx::tmem_ld_wait();
-                        if (vec_ok && (n0 + col0 + c0 + 32 <= a.c_out)) {
-                            epi_block32(a, stage, r0, r1, n0 + col0 + c0, orow_l, rrow_l, bsample, lane);
-                        } else {
-                            epi_chunk16(a, r0, n0 + col0 + c0, orow, rrow, bsample, lane, vec_ok);
-                            epi_chunk16(a, r1, n0 + col0 + c0 + 16, orow, rrow, bsample, lane, vec_ok);
-                        }
-                    }
-                } else {
-                    uint32_t r0[16];
-                    ptx::tmem_ld16(taddr + col0, r0);
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r0[16], r1[16];
+                    ptx::tmem_ld16(taddr + c0, r0);
+                    ptx::tmem_ld16(taddr + c0 + 16, r1);
                     ptx::tmem_ld_wait();
-                    epi_chunk16(a, r0, n0 + col0, orow, rrow, bsample, lane, vec_ok);
+                    if (vec_ok && (n0 + c0 + 32 <= a.c_out)) {
+                        epi_block32(a, stage, r0, r1, n0 + c0, orow_l, rrow_l, bsample, lane);
+                    } else {
+                        epi_chunk16(a, r0, n0 + c0, orow, rrow, bsample, lane, vec_ok);
+                        epi_chunk16(a, r1, n0 + c0 + 16, orow, rrow, bsample, lane, vec_ok);
+                    }
                 }
+            } else {
+                uint32_t r0[16];
+                ptx::tmem_ld16(taddr, r0);
+                ptx::tmem_ld_wait();
+                epi_chunk16(a, r0, n0, orow, rrow, bsample, lane, vec_ok);
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
