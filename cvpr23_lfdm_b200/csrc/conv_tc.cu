@@ -212,9 +212,14 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    constexpr int ACC = 4;                      // TMEM accumulator ring depth (4 x BN <= 512 columns)
-    constexpr uint32_t TMEM_COLS = (ACC * BN <= 32) ? 32 : (ACC * BN <= 64) ? 64 : (ACC * BN <= 128) ? 128 : (ACC * BN <= 256) ? 256 : 512;
-    static_assert(ACC * BN <= 512, "accumulator ring exceeds TMEM");
+    // Each accumulator stage holds TWO column ranges: D1 = A_hi.W_hi + A_lo.W_hi and D2 = A_hi.W_lo.  W_hi / W_lo tiles are
+    // adjacent in smem, so ONE N = 2*BN MMA with A_hi produces (A_hi.W_hi | A_hi.W_lo) while sweeping A_hi once; a second
+    // N = BN MMA adds A_lo.W_hi.  2 MMAs / 14 KiB of operand reads per K-step instead of 3 MMAs / 18 KiB (BN = 64): the
+    // kernel is bound by the 128 B/clk shared-memory port, not by the tensor pipe.  The epilogue sums D1 + D2.
+    constexpr int ACC = (4 * 2 * BN <= 512) ? 4 : 2;      // TMEM accumulator ring depth
+    constexpr uint32_t TMEM_COLS = (ACC * 2 * BN <= 32) ? 32 : (ACC * 2 * BN <= 64) ? 64 : (ACC * 2 * BN <= 128) ? 128 : (ACC * 2 * BN <= 256) ? 256 : 512;
+    static_assert(ACC * 2 * BN <= 512, "accumulator ring exceeds TMEM");
+    constexpr uint32_t IDESC_WIDE = ptx::make_idesc_bf16(BM, 2 * BN);
     constexpr uint32_t IDESC = ptx::make_idesc_bf16(BM, BN);
 
     extern __shared__ uint8_t smem_raw[];
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const uint32_t aphase = (it / ACC) & 1;
             ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
             ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * BN;
+            const uint32_t tmem_d = tmem_base + as * (2 * BN);
             for (int kb = 0; kb < n_kb; ++kb) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
@@ -299,13 +304,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const uint64_t da_hi = ptx::make_sw128_kmajor_desc(sbase);
                     const uint64_t da_lo = ptx::make_sw128_kmajor_desc(sbase + A_BYTES);
                     const uint64_t db_hi = ptx::make_sw128_kmajor_desc(sbase + 2 * A_BYTES);
-                    const uint64_t db_lo = ptx::make_sw128_kmajor_desc(sbase + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
                         const uint64_t off = (uint64_t)(ks * 2);   // 16 bf16 = 32 B, encoded >> 4
-                        ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
-                        ptx::umma_bf16(tmem_d, da_hi + off, db_lo + off, IDESC, 1u);
-                        ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC, 1u);
+                        ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE, (kb > 0 || ks > 0) ? 1u : 0u);  // [W_hi;W_lo]
+                        ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, 1u);                                  // + A_lo.W_hi
                     }
                     ptx::umma_commit(&empty_bar[stage]);
                     if (kb == n_kb - 1) ptx::umma_commit(&tfull_bar[as]);
@@ -350,14 +353,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
             ptx::mbar_wait(&tfull_bar[as], aphase);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN);
             if constexpr (BN >= 32) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r0[16], r1[16];
+                    uint32_t r0[16], r1[16], s0[16], s1[16];
                     ptx::tmem_ld16(taddr + c0, r0);
                     ptx::tmem_ld16(taddr + c0 + 16, r1);
+                    ptx::tmem_ld16(taddr + BN + c0, s0);
+                    ptx::tmem_ld16(taddr + BN + c0 + 16, s1);
                     ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        r0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(s0[j]));
+                        r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(s1[j]));
+                    }
                     if (vec_ok && (n0 + c0 + 32 <= a.c_out)) {
                         epi_block32(a, stage, r0, r1, n0 + c0, orow_l, rrow_l, bsample, lane);
                     } else {
@@ -366,9 +376,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     }
                 }
             } else {
-                uint32_t r0[16];
+                uint32_t r0[16], s0[16];
                 ptx::tmem_ld16(taddr, r0);
+                ptx::tmem_ld16(taddr + BN, s0);
                 ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(s0[j]));
                 epi_chunk16(a, r0, n0, orow, rrow, bsample, lane, vec_ok);
             }
             ptx::tc_fence_before();
