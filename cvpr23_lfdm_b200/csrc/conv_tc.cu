@@ -54,7 +54,7 @@ struct TcArgs {
 
 // epilogue of 16 accumulator columns [nb, nb+16) of one output row
 __device__ __forceinline__ void epi_chunk16(const TcArgs& a, const uint32_t (&rr)[16], int nb, int64_t orow, int64_t rrow,
-                                            int bsample, int lane, bool vec_ok) {
+                                            float* gn_acc, int lane, bool vec_ok) {
     if (nb >= a.c_out) return;       // warp-uniform (padded N)
         float v[16];
 #pragma unroll
@@ -86,14 +86,8 @@ __device__ __forceinline__ void epi_chunk16(const TcArgs& a, const uint32_t (&rr
                 s0 = warp_sum(s0); q0 = warp_sum(q0); s1 = warp_sum(s1); q1 = warp_sum(q1);
                 if (lane == 0) {
                     const int g0 = nb / a.gn_cpg, g1 = (nb + 8) / a.gn_cpg;
-                    double* st = a.gn_stats + (int64_t)bsample * a.gn_groups * 2;
-                    if (g0 == g1) {
-                        atomicAdd(st + g0 * 2, (double)s0 + (double)s1);
-                        atomicAdd(st + g0 * 2 + 1, (double)q0 + (double)q1);
-                    } else {
-                        atomicAdd(st + g0 * 2, (double)s0); atomicAdd(st + g0 * 2 + 1, (double)q0);
-                        atomicAdd(st + g1 * 2, (double)s1); atomicAdd(st + g1 * 2 + 1, (double)q1);
-                    }
+                    atomicAdd(gn_acc + g0 * 2, s0); atomicAdd(gn_acc + g0 * 2 + 1, q0);
+                    atomicAdd(gn_acc + g1 * 2, s1); atomicAdd(gn_acc + g1 * 2 + 1, q1);
                 }
             }
             const int64_t o = orow * a.c_out + nb;
@@ -147,7 +141,7 @@ __device__ __forceinline__ void epi_chunk16(const TcArgs& a, const uint32_t (&rr
 // scattered 16 B accesses per instruction).  `orow_l[i]` / `rrow_l[i]` are the output / residual rows of tile row
 // (lane >> 3) + 4 i of this warp's 32-row slab.
 __device__ __forceinline__ void epi_block32(const TcArgs& a, float* stage, const uint32_t (&r0)[16], const uint32_t (&r1)[16],
-                                            int nb, const int32_t (&orow_l)[8], const int32_t (&rrow_l)[8], int bsample,
+                                            int nb, const int32_t (&orow_l)[8], const int32_t (&rrow_l)[8], float* gn_acc,
                                             int lane) {
     // ---- write: thread = row `lane`, logical 16-byte chunk q -> physical chunk q ^ (lane & 7)
     float4* st4 = reinterpret_cast<float4*>(stage) + lane * 8;
@@ -200,15 +194,14 @@ __device__ __forceinline__ void epi_block32(const TcArgs& a, float* stage, const
         if (lanes_per_group >= 4) { gs += __shfl_xor_sync(0xffffffffu, gs, 2); gq += __shfl_xor_sync(0xffffffffu, gq, 2); }
         if (lanes_per_group >= 8) { gs += __shfl_xor_sync(0xffffffffu, gs, 4); gq += __shfl_xor_sync(0xffffffffu, gq, 4); }
         if (rsub == 0 && (cq % lanes_per_group) == 0) {
-            double* stp = a.gn_stats + ((int64_t)bsample * a.gn_groups + n / a.gn_cpg) * 2;
-            atomicAdd(stp, (double)gs);
-            atomicAdd(stp + 1, (double)gq);
+            atomicAdd(gn_acc + (n / a.gn_cpg) * 2, gs);          // shared-memory accumulators of this epilogue group
+            atomicAdd(gn_acc + (n / a.gn_cpg) * 2 + 1, gq);
         }
     }
     __syncwarp();      // stage is reused by the next block
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool WIDE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -216,9 +209,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // adjacent in smem, so ONE N = 2*BN MMA with A_hi produces (A_hi.W_hi | A_hi.W_lo) while sweeping A_hi once; a second
     // N = BN MMA adds A_lo.W_hi.  2 MMAs / 14 KiB of operand reads per K-step instead of 3 MMAs / 18 KiB (BN = 64): the
     // kernel is bound by the 128 B/clk shared-memory port, not by the tensor pipe.  The epilogue sums D1 + D2.
-    constexpr int ACC = (4 * 2 * BN <= 512) ? 4 : 2;      // TMEM accumulator ring depth
-    constexpr uint32_t TMEM_COLS = (ACC * 2 * BN <= 32) ? 32 : (ACC * 2 * BN <= 64) ? 64 : (ACC * 2 * BN <= 128) ? 128 : (ACC * 2 * BN <= 256) ? 256 : 512;
-    static_assert(ACC * 2 * BN <= 512, "accumulator ring exceeds TMEM");
+    // WIDE = false (K = 1-2 blocks, epilogue-bound GEMMs such as the qkv projections): classic 3 MMAs into one D and a
+    // 4-deep accumulator ring even at BN = 128.
+    constexpr int DCOLS = WIDE ? 2 * BN : BN;             // TMEM columns per accumulator stage
+    constexpr int ACC = (4 * DCOLS <= 512) ? 4 : 2;       // TMEM accumulator ring depth
+    constexpr uint32_t TMEM_COLS = (ACC * DCOLS <= 32) ? 32 : (ACC * DCOLS <= 64) ? 64 : (ACC * DCOLS <= 128) ? 128 : (ACC * DCOLS <= 256) ? 256 : 512;
+    static_assert(ACC * DCOLS <= 512, "accumulator ring exceeds TMEM");
     constexpr uint32_t IDESC_WIDE = ptx::make_idesc_bf16(BM, 2 * BN);
     constexpr uint32_t IDESC = ptx::make_idesc_bf16(BM, BN);
 
@@ -254,12 +250,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int kb_per_tap = a.chunks[0] + a.chunks[1];
     const int n_kb = a.n_taps * kb_per_tap;
     const int total_tiles = a.m_tiles * a.n_tiles;
+    // contiguous tile range per CTA: neighbouring tiles share halo rows in L2 and (almost always) the GroupNorm sample
+    const int t_base = total_tiles / (int)gridDim.x, t_rem = total_tiles % (int)gridDim.x;
+    const int my_first = (int)blockIdx.x * t_base + min((int)blockIdx.x, t_rem);
+    const int my_count = t_base + ((int)blockIdx.x < t_rem ? 1 : 0);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (ptx::elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = my_first; tile < my_first + my_count; ++tile) {
                 const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
                 const int w_t = m_tile % a.tiles_w;
                 const int h_t = (m_tile / a.tiles_w) % a.tiles_h;
@@ -290,12 +290,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // ===================== MMA issuer =====================
         int stage = 0; uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = my_first; tile < my_first + my_count; ++tile, ++it) {
             const int as = it % ACC;
             const uint32_t aphase = (it / ACC) & 1;
             ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
             ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * (2 * BN);
+            const uint32_t tmem_d = tmem_base + as * DCOLS;
             for (int kb = 0; kb < n_kb; ++kb) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
@@ -307,8 +307,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
                         const uint64_t off = (uint64_t)(ks * 2);   // 16 bf16 = 32 B, encoded >> 4
-                        ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE, (kb > 0 || ks > 0) ? 1u : 0u);  // [W_hi;W_lo]
-                        ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, 1u);                                  // + A_lo.W_hi
+                        if constexpr (WIDE) {
+                            ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE, (kb > 0 || ks > 0) ? 1u : 0u);  // [W_hi;W_lo]
+                            ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, 1u);                                  // + A_lo.W_hi
+                        } else {
+                            const uint64_t db_lo = db_hi + (uint64_t)(B_BYTES >> 4);
+                            ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
+                            ptx::umma_bf16(tmem_d, da_hi + off, db_lo + off, IDESC, 1u);
+                            ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC, 1u);
+                        }
                     }
                     ptx::umma_commit(&empty_bar[stage]);
                     if (kb == n_kb - 1) ptx::umma_commit(&tfull_bar[as]);
@@ -324,9 +331,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int r = q * 32 + lane;         // tile row handled by this thread
         const bool vec_ok = (a.c_out % 16) == 0;
         float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 1024;   // 4 KiB per warp
-        for (int it = grp;; it += 2) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            if (tile >= total_tiles) break;
+        float* gn_acc = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + 8 * 4096) + grp * 64;   // [group][32 x (sum, sumsq)]
+        const int tig = threadIdx.x & 127;                     // thread index inside the epilogue group
+        int cur_sample = -1;
+        auto gn_flush = [&](int next_sample) {
+            // all 4 warps of the group are between tiles here (named barrier), so the accumulators are quiescent
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            if (tig < 2 * a.gn_groups) {
+                const float v = gn_acc[tig];
+                if (cur_sample >= 0 && v != 0.f)
+                    atomicAdd(a.gn_stats + (int64_t)cur_sample * a.gn_groups * 2 + tig, (double)v);
+                gn_acc[tig] = 0.f;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            cur_sample = next_sample;
+        };
+        for (int it = grp; it < my_count; it += 2) {
+            const int tile = my_first + it;
             const int as = it % ACC;
             const uint32_t aphase = (it / ACC) & 1;
             const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
@@ -340,7 +361,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const int64_t orow = ((int64_t)nf * a.ho_full + (h * a.mul + a.off_h)) * a.wo_full + (w * a.mul + a.off_w);
             int64_t rrow = orow;
             if (a.res_bcast_f > 0) rrow = (orow / ((int64_t)a.res_bcast_f * a.p_out)) * a.p_out + (orow % a.p_out);
-            const int bsample = a.gn_stats ? (int)(orow / a.rows_per_sample) : 0;
+            if (a.gn_stats) {
+                const int bsample = (int)(__shfl_sync(0xffffffffu, orow, 0) / a.rows_per_sample);   // tile-uniform (128 | rows_per_sample)
+                if (bsample != cur_sample) gn_flush(bsample);
+            }
             // rows this lane handles in the transposed (coalesced) epilogue: tile rows q*32 + (lane>>3) + 4i
             int32_t orow_l[8], rrow_l[8];
 #pragma unroll
@@ -353,40 +377,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
             ptx::mbar_wait(&tfull_bar[as], aphase);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * DCOLS);
             if constexpr (BN >= 32) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t r0[16], r1[16], s0[16], s1[16];
                     ptx::tmem_ld16(taddr + c0, r0);
                     ptx::tmem_ld16(taddr + c0 + 16, r1);
-                    ptx::tmem_ld16(taddr + BN + c0, s0);
-                    ptx::tmem_ld16(taddr + BN + c0 + 16, s1);
+                    if constexpr (WIDE) {
+                        ptx::tmem_ld16(taddr + BN + c0, s0);
+                        ptx::tmem_ld16(taddr + BN + c0 + 16, s1);
+                    }
                     ptx::tmem_ld_wait();
+                    if constexpr (WIDE) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        r0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(s0[j]));
-                        r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(s1[j]));
+                        for (int j = 0; j < 16; ++j) {
+                            r0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(s0[j]));
+                            r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(s1[j]));
+                        }
                     }
                     if (vec_ok && (n0 + c0 + 32 <= a.c_out)) {
-                        epi_block32(a, stage, r0, r1, n0 + c0, orow_l, rrow_l, bsample, lane);
+                        epi_block32(a, stage, r0, r1, n0 + c0, orow_l, rrow_l, gn_acc, lane);
                     } else {
-                        epi_chunk16(a, r0, n0 + c0, orow, rrow, bsample, lane, vec_ok);
-                        epi_chunk16(a, r1, n0 + c0 + 16, orow, rrow, bsample, lane, vec_ok);
+                        epi_chunk16(a, r0, n0 + c0, orow, rrow, gn_acc, lane, vec_ok);
+                        epi_chunk16(a, r1, n0 + c0 + 16, orow, rrow, gn_acc, lane, vec_ok);
                     }
                 }
             } else {
                 uint32_t r0[16], s0[16];
                 ptx::tmem_ld16(taddr, r0);
-                ptx::tmem_ld16(taddr + BN, s0);
+                if constexpr (WIDE) ptx::tmem_ld16(taddr + BN, s0);
                 ptx::tmem_ld_wait();
+                if constexpr (WIDE) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) r0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(s0[j]));
-                epi_chunk16(a, r0, n0, orow, rrow, bsample, lane, vec_ok);
+                    for (int j = 0; j < 16; ++j) r0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(s0[j]));
+                }
+                epi_chunk16(a, r0, n0, orow, rrow, gn_acc, lane, vec_ok);
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
         }
+        if (a.gn_stats) gn_flush(-1);
     }
 
     ptx::tc_fence_before();
@@ -429,13 +460,13 @@ int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims
     return r == CUDA_SUCCESS ? 0 : (1000 + (int)r);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool WIDE>
 int launch(const TcArgs& a, cudaStream_t st) {
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BN * BK * 2;
-    constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 4096;   // + barriers + 8 epilogue staging tiles
+    constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 4096 + 512;   // + barriers + 8 staging tiles + GN accumulators
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
@@ -448,7 +479,7 @@ int launch(const TcArgs& a, cudaStream_t st) {
     }
     int total = a.m_tiles * a.n_tiles;
     int grid = total < num_sms ? total : num_sms;
-    conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, SMEM, st>>>(a);
+    conv_tc_kernel<BN, STAGES, WIDE><<<grid, NUM_THREADS, SMEM, st>>>(a);
     LFDM_CHECK_LAUNCH();
     return 0;
 }
@@ -501,7 +532,7 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
     else if (d->c_out <= 16) bn = 16;
     else return LFDM_E_UNSUPP;
     const int c_out_pad = ((d->c_out + bn - 1) / bn) * bn;
-    if (d->gn_stats && ((d->gn_cpg % 8) != 0 || d->rows_per_sample % 128 != 0 || mul != 1)) return LFDM_E_UNSUPP;
+    if (d->gn_stats && ((d->gn_cpg % 8) != 0 || d->rows_per_sample % 128 != 0 || mul != 1 || d->c_out / d->gn_cpg > 32)) return LFDM_E_UNSUPP;
 
     TcArgs a;
     memset(&a, 0, sizeof(a));
@@ -583,11 +614,13 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
             for (int t = 0; t < 4; ++t) { a.tap_map[t] = 0; a.tap_dy[t] = (int8_t)dyl[t >> 1]; a.tap_dx[t] = (int8_t)dxl[t & 1]; }
         }
         int rc;
+        const int n_kb = taps_per_launch * (a.chunks[0] + a.chunks[1]);
+        const bool wide = n_kb >= 3;          // MMA/smem-bound tiles: wide 2-MMA scheme; short-K GEMMs: deeper accumulator ring
         switch (bn) {
-            case 128: rc = launch<128, 3>(a, st); break;
-            case 64: rc = launch<64, 4>(a, st); break;
-            case 32: rc = launch<32, 4>(a, st); break;
-            default: rc = launch<16, 4>(a, st); break;
+            case 128: rc = wide ? launch<128, 3, true>(a, st) : launch<128, 3, false>(a, st); break;
+            case 64: rc = wide ? launch<64, 4, true>(a, st) : launch<64, 4, false>(a, st); break;
+            case 32: rc = launch<32, 4, true>(a, st); break;
+            default: rc = launch<16, 4, true>(a, st); break;
         }
         if (rc) return rc;
     }
