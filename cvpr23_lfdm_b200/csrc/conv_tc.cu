@@ -250,16 +250,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int kb_per_tap = a.chunks[0] + a.chunks[1];
     const int n_kb = a.n_taps * kb_per_tap;
     const int total_tiles = a.m_tiles * a.n_tiles;
-    // contiguous tile range per CTA: neighbouring tiles share halo rows in L2 and (almost always) the GroupNorm sample
-    const int t_base = total_tiles / (int)gridDim.x, t_rem = total_tiles % (int)gridDim.x;
-    const int my_first = (int)blockIdx.x * t_base + min((int)blockIdx.x, t_rem);
-    const int my_count = t_base + ((int)blockIdx.x < t_rem ? 1 : 0);
+    // tiles are dealt round-robin: at any instant the CTAs sweep ~gridDim consecutive tiles, i.e. one contiguous window of the
+    // activation tensor (measured ~8 % faster than giving every CTA its own contiguous range: DRAM/L2 locality across CTAs)
+    const int my_count = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (ptx::elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = my_first; tile < my_first + my_count; ++tile) {
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
                 const int w_t = m_tile % a.tiles_w;
                 const int h_t = (m_tile / a.tiles_w) % a.tiles_h;
@@ -290,7 +289,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // ===================== MMA issuer =====================
         int stage = 0; uint32_t phase = 0;
         int it = 0;
-        for (int tile = my_first; tile < my_first + my_count; ++tile, ++it) {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int as = it % ACC;
             const uint32_t aphase = (it / ACC) & 1;
             ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -347,7 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             cur_sample = next_sample;
         };
         for (int it = grp; it < my_count; it += 2) {
-            const int tile = my_first + it;
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int as = it % ACC;
             const uint32_t aphase = (it / ACC) & 1;
             const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
