@@ -56,13 +56,17 @@ __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restri
 
     // gather: 3 tensors x L rows x 8 segments of 16 B, all in flight at once (cp.async), pad rows zeroed
     {
-        const int nseg = 3 * L * 8;
-        for (int idx = lane; idx < nseg; idx += 32) {
-            const int t = idx / (L * 8);
-            const int rem = idx - t * (L * 8);
-            const int j = rem >> 3, seg = rem & 7;
-            const float* src = qkv + (base + (int64_t)j * row_stride) * (3 * hid) + t * hid + h * DH + seg * 4;
-            cp_async16(sq + t * LP * QP + j * QP + seg * 4, src);
+        // (no runtime divisions: t is an outer loop, row = idx >> 3, segment = idx & 7)
+        const float* src0 = qkv + base * (3 * hid) + h * DH;
+        const int64_t rstep = row_stride * (3 * hid);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            float* dst = sq + t * LP * QP;
+            const float* srct = src0 + t * hid;
+            for (int idx = lane; idx < L * 8; idx += 32) {
+                const int j = idx >> 3, seg = idx & 7;
+                cp_async16(dst + j * QP + seg * 4, srct + (int64_t)j * rstep + seg * 4);
+            }
         }
         cp_async_commit();
         for (int idx = lane; idx < 3 * (LP - L) * 8; idx += 32) {

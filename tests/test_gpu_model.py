@@ -249,3 +249,17 @@ def test_full_unet_256res_geometry_vs_oracle(full_model):
     ref = O.unet3d_forward(sd, x, t, cond)
     got = full_model.unet(x.cuda(), t.cuda(), cond=cond.cuda())
     close(got, ref, "full UNet @ 64x64 latent")
+
+
+def test_full_decode_256res_vs_oracle(full_model):
+    """MUG-256 decode geometry: 256x256 frames, 64x64 latent flow (W = 256 -> two 128-wide conv tiles per row)"""
+    from oracle import lfdm_oracle as O
+    g = torch.Generator().manual_seed(88)
+    img = torch.rand(1, 3, 256, 256, generator=g)
+    flow = torch.rand(1, 64, 64, 2, generator=g) * 2.2 - 1.1
+    occ = torch.rand(1, 1, 64, 64, generator=g)
+    gsd = {k: v.detach().cpu() for k, v in full_model.generator.state_dict().items()}
+    ref = O.generator_forward_with_flow(gsd, img, flow, occ)
+    got = full_model.generator.forward_with_flow(img.cuda(), flow.cuda(), occ.cuda())
+    close(got["deformed"], ref["deformed"], "256-res deformed")
+    close(got["prediction"], ref["prediction"], "256-res prediction")
