@@ -53,31 +53,44 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
         s_mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
     }
     __syncthreads();
+    const bool quad_params = (cpg & 3) == 0;      // the 4 channels of a float4 share one group: vector parameter loads
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t row = i / c4;
-        int ch = (int)(i - row * c4) * 4;
-        int b = (int)(row / rows_per_sample);
-        float4 v = *reinterpret_cast<const float4*>(x + row * c + ch);
+        const int64_t row = i / c4;
+        const int ch = (int)(i - row * c4) * 4;
+        const int b = (int)(row / rows_per_sample);
+        const float4 v = *reinterpret_cast<const float4*>(x + row * c + ch);
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (residual) q = *reinterpret_cast<const float4*>(residual + row * c + ch);
         float vv[4] = {v.x, v.y, v.z, v.w};
         float r[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            int cc = ch + e;
-            int g = cc / cpg;
-            float2 mr = s_mr[b * groups + g];
-            float mean = mr.x, rstd = mr.y;
-            float y = (vv[e] - mean) * rstd * gamma[cc] + beta[cc];
+        if (quad_params) {
+            const float2 mr = s_mr[b * groups + ch / cpg];
+            const float4 g4 = *reinterpret_cast<const float4*>(gamma + ch), b4 = *reinterpret_cast<const float4*>(beta + ch);
+            const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
             if (ss) {
-                float sc = ss[(int64_t)b * ss_stride + cc], sh = ss[(int64_t)b * ss_stride + c + cc];
-                y = y * (sc + 1.f) + sh;
+                const float4 s4 = *reinterpret_cast<const float4*>(ss + (int64_t)b * ss_stride + ch);
+                const float4 h4 = *reinterpret_cast<const float4*>(ss + (int64_t)b * ss_stride + c + ch);
+                sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+                sh[0] = h4.x; sh[1] = h4.y; sh[2] = h4.z; sh[3] = h4.w;
             }
-            r[e] = silu_f(y);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float y = (vv[e] - mr.x) * mr.y * gg[e] + bb[e];
+                if (ss) y = y * (sc[e] + 1.f) + sh[e];
+                r[e] = silu_f(y);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int cc = ch + e;
+                const float2 mr = s_mr[b * groups + cc / cpg];
+                float y = (vv[e] - mr.x) * mr.y * gamma[cc] + beta[cc];
+                if (ss) y = y * (ss[(int64_t)b * ss_stride + cc] + 1.f) + ss[(int64_t)b * ss_stride + c + cc];
+                r[e] = silu_f(y);
+            }
         }
-        if (residual) {
-            float4 q = *reinterpret_cast<const float4*>(residual + row * c + ch);
-            r[0] += q.x; r[1] += q.y; r[2] += q.z; r[3] += q.w;
-        }
-        float4 o = make_float4(r[0], r[1], r[2], r[3]);
+        const float4 o = make_float4(r[0] + q.x, r[1] + q.y, r[2] + q.z, r[3] + q.w);
         if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * c + ch) = o;
         if (out_sb) store_sb4(out_sb, out_plane, row * c + ch, o);
     }
