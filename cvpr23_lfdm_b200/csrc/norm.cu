@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
         s_mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
     }
     __syncthreads();
-    const bool quad_params = (cpg & 3) == 0;      // the 4 channels of a float4 share one group: vector parameter loads
+    // the 4 channels of a float4 share one group and every parameter vector is 16-byte aligned: vector parameter loads
+    const bool quad_params = (cpg & 3) == 0 && ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0 &&
+                             (ss == nullptr || ((reinterpret_cast<uintptr_t>(ss) & 15) == 0 && (ss_stride & 3) == 0));
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = i / c4;
         const int ch = (int)(i - row * c4) * 4;
