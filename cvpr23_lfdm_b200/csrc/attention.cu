@@ -653,6 +653,7 @@ __device__ __forceinline__ void issue_rows(float* dst, const float* src_col, int
     }
 }
 
+template <bool USE_MMA>
 __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
                                                                  int64_t out_plane, float* __restrict__ out_f32, int n_pos,
                                                                  int heads) {
@@ -691,6 +692,13 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) ctx[i][j] = 0.f;
+    float cacc[2][4][4];                                  // mma C fragments of the context (USE_MMA)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cacc[mt][nt][e] = 0.f;
     float den = 0.f;
     const int n_chunks = (n_pos + 31) / 32;
     if (w < n_chunks) {
@@ -719,16 +727,46 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
         }
         __syncwarp();
         const int rows = min(32, n_pos - n0);
-#pragma unroll 4
-        for (int r = 0; r < rows; ++r) {
-            const float4 e0 = *reinterpret_cast<const float4*>(kt + r * TP + 8 * a);
-            const float4 e1 = *reinterpret_cast<const float4*>(kt + r * TP + 8 * a + 4);
-            const float4 v = *reinterpret_cast<const float4*>(vt + r * TP + 4 * b);
-            const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+        if constexpr (USE_MMA) {
+            // ctx (32 x 32) += ek^T (32 x 32 rows) . v : split-bf16 mma.m16n8k16, A(m = d, k = n) = ek[n][d], B(k = n, n = e) = v[n][e]
+            float* vtw = const_cast<float*>(vt);
+            for (int r = rows; r < 32; ++r) vtw[r * TP + lane] = 0.f;      // ragged last chunk: no stale rows in the product
+            __syncwarp();
+            const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                ctx[i][0] = fmaf(ev[i], v.x, ctx[i][0]); ctx[i][1] = fmaf(ev[i], v.y, ctx[i][1]);
-                ctx[i][2] = fmaf(ev[i], v.z, ctx[i][2]); ctx[i][3] = fmaf(ev[i], v.w, ctx[i][3]);
+            for (int ks = 0; ks < 2; ++ks) {
+                const int n_lo = 16 * ks + 2 * t;
+                uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int e = g + 8 * nt;
+                    split_bf16x2(vt[n_lo * TP + e], vt[(n_lo + 1) * TP + e], bh[nt][0], bl[nt][0]);
+                    split_bf16x2(vt[(n_lo + 8) * TP + e], vt[(n_lo + 9) * TP + e], bh[nt][1], bl[nt][1]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int d0 = g + 16 * mt;
+                    uint32_t ah[4], al[4];
+                    split_bf16x2(kt[n_lo * TP + d0], kt[(n_lo + 1) * TP + d0], ah[0], al[0]);
+                    split_bf16x2(kt[n_lo * TP + d0 + 8], kt[(n_lo + 1) * TP + d0 + 8], ah[1], al[1]);
+                    split_bf16x2(kt[(n_lo + 8) * TP + d0], kt[(n_lo + 9) * TP + d0], ah[2], al[2]);
+                    split_bf16x2(kt[(n_lo + 8) * TP + d0 + 8], kt[(n_lo + 9) * TP + d0 + 8], ah[3], al[3]);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) mma3_bf16(cacc[mt][nt], ah, al, bh[nt], bl[nt]);
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) {
+                const float4 e0 = *reinterpret_cast<const float4*>(kt + r * TP + 8 * a);
+                const float4 e1 = *reinterpret_cast<const float4*>(kt + r * TP + 8 * a + 4);
+                const float4 v = *reinterpret_cast<const float4*>(vt + r * TP + 4 * b);
+                const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    ctx[i][0] = fmaf(ev[i], v.x, ctx[i][0]); ctx[i][1] = fmaf(ev[i], v.y, ctx[i][1]);
+                    ctx[i][2] = fmaf(ev[i], v.z, ctx[i][2]); ctx[i][3] = fmaf(ev[i], v.w, ctx[i][3]);
+                }
             }
         }
         __syncwarp();
@@ -736,9 +774,20 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
     cp_async_wait<0>();
     __syncthreads();                                     // all tiles consumed: alias the buffer as [LW][32][32]
     float* s_ctx = s_dynl;
+    if constexpr (USE_MMA) {
+        const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<float4*>(s_ctx + (w * DH + 8 * a + i) * DH + 4 * b) = make_float4(ctx[i][0], ctx[i][1], ctx[i][2], ctx[i][3]);
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                *reinterpret_cast<float2*>(s_ctx + (w * DH + g + 16 * mt) * DH + 8 * nt + 2 * t) = make_float2(cacc[mt][nt][0], cacc[mt][nt][1]);
+                *reinterpret_cast<float2*>(s_ctx + (w * DH + g + 16 * mt + 8) * DH + 8 * nt + 2 * t) = make_float2(cacc[mt][nt][2], cacc[mt][nt][3]);
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(s_ctx + (w * DH + 8 * a + i) * DH + 4 * b) = make_float4(ctx[i][0], ctx[i][1], ctx[i][2], ctx[i][3]);
+    }
     s_red[w][lane] = den;
     __syncthreads();
     for (int i = threadIdx.x; i < DH * DH; i += 32 * LW) {
@@ -749,10 +798,23 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
         s_ctxn[d][e] = acc / dd;                         // softmax normalisation of k folded into the context
     }
     __syncthreads();
+    uint32_t pbh[2][4][2], pbl[2][4][2];                  // B fragments of ctxn (k = d, n = e), kept for the whole phase 3
+    if constexpr (USE_MMA) {
+        const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float4 t = *reinterpret_cast<const float4*>(&s_ctxn[8 * a + i][4 * b]);
-        ctx[i][0] = t.x; ctx[i][1] = t.y; ctx[i][2] = t.z; ctx[i][3] = t.w;
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int d0 = 16 * ks + 2 * t, e = g + 8 * nt;
+                split_bf16x2(s_ctxn[d0][e], s_ctxn[d0 + 1][e], pbh[ks][nt][0], pbl[ks][nt][0]);
+                split_bf16x2(s_ctxn[d0 + 8][e], s_ctxn[d0 + 9][e], pbh[ks][nt][1], pbl[ks][nt][1]);
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(&s_ctxn[8 * a + i][4 * b]);
+            ctx[i][0] = t.x; ctx[i][1] = t.y; ctx[i][2] = t.z; ctx[i][3] = t.w;
+        }
     }
     __syncthreads();                                     // s_ctxn (aliased) fully consumed before q tiles land on it
 
@@ -789,26 +851,71 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
         }
         __syncwarp();
         const int rows = min(32, n_pos - n0);
-#pragma unroll 2
-        for (int r = 0; r < rows; ++r) {
-            const float4 q0 = *reinterpret_cast<const float4*>(qt + r * TP + 8 * a);
-            const float4 q1 = *reinterpret_cast<const float4*>(qt + r * TP + 8 * a + 4);
-            const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (USE_MMA) {
+            // out (32 rows x 32) = qs (32 x 32) . ctxn : A(m = n, k = d) from the tile, B fragments resident in registers
+            const int g = lane >> 2, t = lane & 3;
+            float oacc[2][4][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                o.x = fmaf(ctx[i][0], qv[i], o.x); o.y = fmaf(ctx[i][1], qv[i], o.y);
-                o.z = fmaf(ctx[i][2], qv[i], o.z); o.w = fmaf(ctx[i][3], qv[i], o.w);
-            }
-            // reduce over the four d-blocks (lanes that share b)
-            o.x += __shfl_xor_sync(0xffffffffu, o.x, 8);  o.y += __shfl_xor_sync(0xffffffffu, o.y, 8);
-            o.z += __shfl_xor_sync(0xffffffffu, o.z, 8);  o.w += __shfl_xor_sync(0xffffffffu, o.w, 8);
-            o.x += __shfl_xor_sync(0xffffffffu, o.x, 16); o.y += __shfl_xor_sync(0xffffffffu, o.y, 16);
-            o.z += __shfl_xor_sync(0xffffffffu, o.z, 16); o.w += __shfl_xor_sync(0xffffffffu, o.w, 16);
-            if (a == 0) {
-                const int64_t oi = (fr * n_pos + n0 + r) * hid + h * DH + 4 * b;
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) oacc[mt][nt][e] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r0 = g + 16 * mt, dcol = 16 * ks + 2 * t;
+                    const float2 x0 = *reinterpret_cast<const float2*>(qt + r0 * TP + dcol);
+                    const float2 x1 = *reinterpret_cast<const float2*>(qt + (r0 + 8) * TP + dcol);
+                    const float2 x2 = *reinterpret_cast<const float2*>(qt + r0 * TP + dcol + 8);
+                    const float2 x3 = *reinterpret_cast<const float2*>(qt + (r0 + 8) * TP + dcol + 8);
+                    uint32_t ah[4], al[4];
+                    split_bf16x2(x0.x, x0.y, ah[0], al[0]);
+                    split_bf16x2(x1.x, x1.y, ah[1], al[1]);
+                    split_bf16x2(x2.x, x2.y, ah[2], al[2]);
+                    split_bf16x2(x3.x, x3.y, ah[3], al[3]);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) mma3_bf16(oacc[mt][nt], ah, al, pbh[ks][nt], pbl[ks][nt]);
+                }
+            __syncwarp();                                  // all lanes done reading qs: stage the outputs in the same tile
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    *reinterpret_cast<float2*>(qt + (g + 16 * mt) * TP + 8 * nt + 2 * t) = make_float2(oacc[mt][nt][0], oacc[mt][nt][1]);
+                    *reinterpret_cast<float2*>(qt + (g + 16 * mt + 8) * TP + 8 * nt + 2 * t) = make_float2(oacc[mt][nt][2], oacc[mt][nt][3]);
+                }
+            __syncwarp();
+            for (int idx = lane; idx < rows * 8; idx += 32) {
+                const int r = idx >> 3, seg = idx & 7;
+                const float4 o = *reinterpret_cast<const float4*>(qt + r * TP + seg * 4);
+                const int64_t oi = (fr * n_pos + n0 + r) * hid + h * DH + seg * 4;
                 if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi) = o;
                 if (out_sb) store_sb4(out_sb, out_plane, oi, o);
+            }
+        } else {
+#pragma unroll 2
+            for (int r = 0; r < rows; ++r) {
+                const float4 q0 = *reinterpret_cast<const float4*>(qt + r * TP + 8 * a);
+                const float4 q1 = *reinterpret_cast<const float4*>(qt + r * TP + 8 * a + 4);
+                const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    o.x = fmaf(ctx[i][0], qv[i], o.x); o.y = fmaf(ctx[i][1], qv[i], o.y);
+                    o.z = fmaf(ctx[i][2], qv[i], o.z); o.w = fmaf(ctx[i][3], qv[i], o.w);
+                }
+                // reduce over the four d-blocks (lanes that share b)
+                o.x += __shfl_xor_sync(0xffffffffu, o.x, 8);  o.y += __shfl_xor_sync(0xffffffffu, o.y, 8);
+                o.z += __shfl_xor_sync(0xffffffffu, o.z, 8);  o.w += __shfl_xor_sync(0xffffffffu, o.w, 8);
+                o.x += __shfl_xor_sync(0xffffffffu, o.x, 16); o.y += __shfl_xor_sync(0xffffffffu, o.y, 16);
+                o.z += __shfl_xor_sync(0xffffffffu, o.z, 16); o.w += __shfl_xor_sync(0xffffffffu, o.w, 16);
+                if (a == 0) {
+                    const int64_t oi = (fr * n_pos + n0 + r) * hid + h * DH + 4 * b;
+                    if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi) = o;
+                    if (out_sb) store_sb4(out_sb, out_plane, oi, o);
+                }
             }
         }
         __syncwarp();
@@ -898,12 +1005,18 @@ extern "C" int lfdm_attn_linear(const float* qkv, void* out_sb, int64_t out_plan
     const size_t smem = sizeof(float) * LW * 4 * TILE;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attn_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    attn_linear_kernel<<<(unsigned)(n_frames * heads), 32 * LW, smem, (cudaStream_t)stream>>>(qkv, (bf16*)out_sb, out_plane,
-                                                                                             out_f32, n_pos, heads);
+    static const bool use_mma = (getenv("LFDM_ATTN_SIMT") == nullptr);          // A/B switch: CUDA-core tiling instead
+    if (use_mma)
+        attn_linear_kernel<true><<<(unsigned)(n_frames * heads), 32 * LW, smem, (cudaStream_t)stream>>>(
+            qkv, (bf16*)out_sb, out_plane, out_f32, n_pos, heads);
+    else
+        attn_linear_kernel<false><<<(unsigned)(n_frames * heads), 32 * LW, smem, (cudaStream_t)stream>>>(
+            qkv, (bf16*)out_sb, out_plane, out_f32, n_pos, heads);
     LFDM_CHECK_LAUNCH();
     return 0;
 }
