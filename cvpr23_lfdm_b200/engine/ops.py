@@ -99,7 +99,7 @@ class ConvLayer:
         return 2 * h + 2 * self.pad - self.kh + 1, 2 * w + 2 * self.pad - self.kw + 1
 
     def __call__(self, srcs, nf, h, w, *, out_f32=None, out_sb=None, residual=None, res_bcast_f=0, f32_act=0,
-                 sb_act=0, sb_scale=None, sb_shift=None, gn_stats=None, gn_groups=8, rows_per_sample=0):
+                 sb_act=0, sb_scale=None, sb_shift=None, gn_stats=None, gn_groups=8, rows_per_sample=0, stats_zeroed=False):
         """srcs: list of SB or F32 row matrices (one per virtual-concat source)."""
         ho, wo = self.out_hw(h, w)
         a_sb = [None, None]
@@ -135,7 +135,8 @@ class ConvLayer:
             if fused_stats:
                 cpg = self.cout // gn_groups
                 if cpg % 8 == 0 and rows_per_sample % 128 == 0 and self.mode == L.CONV_DIRECT:
-                    gn_stats.zero_()
+                    if not stats_zeroed:
+                        gn_stats.zero_()
                     kw["gn_stats"] = gn_stats
                     kw["gn_cpg"] = cpg
                 else:

@@ -221,15 +221,14 @@ class UnetEngine:
         dev = self.dev
         m = nf * h * w
         c = r.c_out
-        stats = torch.empty((b, r.groups, 2), dtype=torch.float64, device=dev)
+        stats, stats2 = self._next_stats(b, r.groups), self._next_stats(b, r.groups)
         h1 = f32(m, c, dev)
-        r.conv1(srcs_sb, nf, h, w, out_f32=h1, gn_stats=stats, gn_groups=r.groups, rows_per_sample=rps)
+        r.conv1(srcs_sb, nf, h, w, out_f32=h1, gn_stats=stats, gn_groups=r.groups, rows_per_sample=rps, stats_zeroed=True)
         a1 = SB(m, c, dev)
         ss_view = ss[:, r.ss_off:r.ss_off + 2 * c] if r.has_mlp else None
         ops.gn_apply(h1, stats, r.g1, r.b1, ss_view, None, None, a1, r.groups, rps, r.eps)
-        stats2 = torch.empty((b, r.groups, 2), dtype=torch.float64, device=dev)
         h2 = h1  # reuse buffer: conv1 output is dead after gn_apply
-        r.conv2([a1], nf, h, w, out_f32=h2, gn_stats=stats2, gn_groups=r.groups, rows_per_sample=rps)
+        r.conv2([a1], nf, h, w, out_f32=h2, gn_stats=stats2, gn_groups=r.groups, rows_per_sample=rps, stats_zeroed=True)
         if r.res is not None:
             res = f32(m, c, dev)
             r.res(srcs_sb, nf, h, w, out_f32=res)
@@ -330,8 +329,19 @@ class UnetEngine:
         lx([cols], b * f, h, w, out_f32=x0, out_sb=x0_sb, residual=fea_conv, res_bcast_f=f)
         return self._body(x0, x0_sb, ss, b, f, h, w)
 
+    def _next_stats(self, b, groups):
+        """GroupNorm accumulators of one evaluation come from one pool zeroed by a single fill (not one per conv)"""
+        n = b * groups * 2
+        if self._stats_pool is None or self._stats_off + n > self._stats_pool.numel():
+            self._stats_pool = torch.zeros(max(64 * n, 4096), dtype=torch.float64, device=self.dev)
+            self._stats_off = 0
+        t = self._stats_pool[self._stats_off:self._stats_off + n].view(b, groups, 2)
+        self._stats_off += n
+        return t
+
     def _body(self, r_f32, r_sb, ss, b, f, h, w):
         nf = b * f
+        self._stats_pool, self._stats_off = None, 0
         self._tap("init_conv", r_f32, b, f, h, w)
         x, x_sb = self._temporal(self.init_tattn, r_f32, b, f, h, w, want_sb=True)
         self._tap("init", x, b, f, h, w)

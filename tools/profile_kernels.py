@@ -77,7 +77,7 @@ def cases():
         ang = torch.outer(torch.arange(F, device=dev).float(), 1.0 / (10000 ** (torch.arange(0, 32, 2, device=dev).float() / 32)))
         cs, sn, bias = ang.cos().contiguous(), ang.sin().contiguous(), torch.randn(heads, F, F, device=dev)
         run = lambda: ops.attn_softmax(qkv, o, None, B * p, F, heads, p, F * p, 1, p, cs, sn, bias)
-        return run, 4.0 * B * p * heads * F * F * 32, m * 768 * 4 + m * 256 * 4, lambda: "simt"
+        return run, 4.0 * B * p * heads * F * F * 32, m * 768 * 4 + m * 256 * 4, lambda: "mma.sync split-bf16"
     c["attn_temporal_32"] = attn_t
 
     def attn_l():
@@ -86,7 +86,7 @@ def cases():
         qkv = torch.randn(m, 768, device=dev)
         o = SB(m, 256, dev)
         run = lambda: ops.attn_linear(qkv, o, None, B * F, p, heads)
-        return run, 4.0 * B * F * heads * 32 * 32 * p, m * 768 * 4 * (4 / 3) + m * 256 * 4, lambda: "simt"
+        return run, 4.0 * B * F * heads * 32 * 32 * p, m * 768 * 4 * (4 / 3) + m * 256 * 4, lambda: "mma.sync split-bf16"
     c["attn_linear_32"] = attn_l
 
     def gn():
