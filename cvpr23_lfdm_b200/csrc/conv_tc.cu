@@ -15,6 +15,7 @@
 // Replaces cuDNN/cuBLAS behind every Conv3d(1,k,k)/ConvTranspose3d/Conv2d/Linear on the path (include/lfdm_b200.h).
 #include <cuda.h>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -29,6 +30,8 @@ constexpr int NUM_THREADS = 384;     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, 
 struct TcArgs {
     CUtensorMap tmA[8];              // [source*4 + parity view]
     CUtensorMap tmB;
+    CUtensorMap tmOut;               // fp32 [M][c_out], box {32 cols, 32 rows}, 128B swizzle (TMA-store epilogue)
+    int32_t tma_store;
     int32_t n_taps, tap_base;
     int8_t tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
     int32_t chunks[2];               // 64-channel chunks per source
@@ -220,7 +223,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    // [operand ring][8 x 4 KiB epilogue staging (1024-aligned: TMA-store / swizzle atoms)][barriers][GN accumulators]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 8 * 4096);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + ACC;
@@ -232,6 +236,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (warp == 0 && ptx::elect_one()) {
         for (int i = 0; i < 8; ++i) ptx::prefetch_tensormap(&a.tmA[i]);
         ptx::prefetch_tensormap(&a.tmB);
+        if (a.tma_store) ptx::prefetch_tensormap(&a.tmOut);
     }
     if (warp == 1 && ptx::elect_one()) {
         for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
@@ -329,8 +334,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int grp = (warp - 4) >> 2;     // two epilogue groups of 4 warps drain alternate tiles concurrently
         const int r = q * 32 + lane;         // tile row handled by this thread
         const bool vec_ok = (a.c_out % 16) == 0;
-        float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 4) * 1024;   // 4 KiB per warp
-        float* gn_acc = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + 8 * 4096) + grp * 64;   // [group][32 x (sum, sumsq)]
+        float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - 4) * 1024;          // 4 KiB per warp
+        float* gn_acc = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 8 * 4096 + 256) + grp * 64;   // [group][32 x (sum, sumsq)]
         const int tig = threadIdx.x & 127;                     // thread index inside the epilogue group
         int cur_sample = -1;
         auto gn_flush = [&](int next_sample) {
@@ -395,7 +400,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(s1[j]));
                         }
                     }
-                    if (vec_ok && (n0 + c0 + 32 <= a.c_out)) {
+                    if (a.tma_store) {
+                        // plain F32 output (+bias, +GroupNorm sums): thread-per-row -> swizzled smem -> one TMA store per
+                        // 32x32 block; the warp never waits for its global stores
+                        const int nb = n0 + c0;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r0[j]); v[16 + j] = __uint_as_float(r1[j]); }
+                        if (a.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(a.bias + nb + j);
+                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            }
+                        }
+                        if (a.gn_stats) {
+#pragma unroll
+                            for (int oct = 0; oct < 4; ++oct) {        // cpg is a multiple of 8: one (sum, sumsq) per 8 columns
+                                float s8 = 0.f, q8 = 0.f;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { s8 += v[8 * oct + j]; q8 = fmaf(v[8 * oct + j], v[8 * oct + j], q8); }
+                                s8 = warp_sum(s8); q8 = warp_sum(q8);
+                                if (lane == 0) {
+                                    const int gi = (nb + 8 * oct) / a.gn_cpg;
+                                    atomicAdd(gn_acc + gi * 2, s8); atomicAdd(gn_acc + gi * 2 + 1, q8);
+                                }
+                            }
+                        }
+                        if (lane == 0) ptx::tma_store_wait_read0();      // previous store has finished reading this stage
+                        __syncwarp();
+                        float4* st4 = reinterpret_cast<float4*>(stage) + lane * 8;
+                        const int sw = lane & 7;
+#pragma unroll
+                        for (int qd = 0; qd < 8; ++qd) st4[qd ^ sw] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&a.tmOut, stage, nb, orow_l[0]);     // lane 0: orow_l[0] = first row of this warp's slab
+                            ptx::tma_store_commit();
+                        }
+                    } else if (vec_ok && (n0 + c0 + 32 <= a.c_out)) {
                         epi_block32(a, stage, r0, r1, n0 + c0, orow_l, rrow_l, gn_acc, lane);
                     } else {
                         epi_chunk16(a, r0, n0 + c0, orow, rrow, gn_acc, lane, vec_ok);
@@ -417,6 +461,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             ptx::mbar_arrive(&tempty_bar[as]);
         }
         if (a.gn_stats) gn_flush(-1);
+        if (a.tma_store && lane == 0) ptx::tma_store_wait0();
     }
 
     ptx::tc_fence_before();
@@ -449,11 +494,11 @@ PFN_encodeTiled get_encode() {
 }
 
 int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box) {
+             const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return LFDM_E_NODRIVER;
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+    CUresult r = enc(tm, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims,
                      strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (1000 + (int)r);
@@ -462,7 +507,7 @@ int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims
 template <int BN, int STAGES, bool WIDE>
 int launch(const TcArgs& a, cudaStream_t st) {
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BN * BK * 2;
-    constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 4096 + 512;   // + barriers + 8 staging tiles + GN accumulators
+    constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 8 * 4096 + 256 + 512;   // + 8 staging tiles + barriers + GN accumulators
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -564,6 +609,21 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
         cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bn, 1, 1};
         int rc = make_map(&a.tmB, d->w_sb, 4, dims, strides, box);
         if (rc) return rc;
+    }
+    // ---- TMA-store epilogue: plain F32 output (+bias, +GroupNorm sums), consecutive output rows per tile
+    a.tma_store = 0;
+    {
+        static const bool allow = (getenv("LFDM_CONV_NO_TMA_STORE") == nullptr);     // A/B switch
+        const int64_t m_out = (int64_t)d->nf * d->h_out * d->w_out;
+        if (allow && d->out_f32 && !d->out_sb && !d->residual && d->f32_act == LFDM_ACT_NONE && mul == 1 && bn >= 32 &&
+            d->c_out % 32 == 0 && (reinterpret_cast<uintptr_t>(d->out_f32) & 15) == 0) {
+            cuuint64_t dims[2] = {(cuuint64_t)d->c_out, (cuuint64_t)m_out};
+            cuuint64_t strides[1] = {(cuuint64_t)d->c_out * 4};
+            cuuint32_t box[2] = {32, 32};
+            int rc = make_map(&a.tmOut, d->out_f32, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+            if (rc) return rc;
+            a.tma_store = 1;
+        }
     }
     a.chunks[0] = d->a_c[0] / BK;
     a.chunks[1] = nsrc > 1 ? d->a_c[1] / BK : 0;

@@ -56,7 +56,7 @@ def ref_conv(x, w, b, mode, stride, pad, reflect):
 
 
 def run_conv(engine, n, cins, cout, h, w, k, pad, mode=0, stride=1, reflect=False, bias=True, residual=False,
-             res_bcast=0, f32_act=0, sb_aff=False, sb_act=0, gn_groups=0, a_f32=False, seed=0, fps=1):
+             res_bcast=0, f32_act=0, sb_aff=False, sb_act=0, gn_groups=0, a_f32=False, seed=0, fps=1, f32_only=False):
     from cvpr23_lfdm_b200 import _lib as L
     from cvpr23_lfdm_b200.engine.ops import ConvLayer, f32
     from cvpr23_lfdm_b200._lib import SB
@@ -90,7 +90,7 @@ def run_conv(engine, n, cins, cout, h, w, k, pad, mode=0, stride=1, reflect=Fals
             res_rows = rows_of(r4).to(dev())
             yv = rows_of(y + r4)
     out_f32 = f32(m_out, cout, dev())
-    out_sb = SB(m_out, cout, dev())
+    out_sb = None if f32_only else SB(m_out, cout, dev())
     sc = sh = None
     if sb_aff:
         sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
@@ -106,7 +106,8 @@ def run_conv(engine, n, cins, cout, h, w, k, pad, mode=0, stride=1, reflect=Fals
     u = yv
     if sb_aff:
         u = u * sc[None] + sh[None]
-    close(out_sb.float(), act[sb_act](u), "out_sb", rtol=RTOL, atol=ATOL)
+    if out_sb is not None:
+        close(out_sb.float(), act[sb_act](u), "out_sb", rtol=RTOL, atol=ATOL)
     if gn_groups:
         cpg = cout // gn_groups
         v = yv.reshape(n // fps, fps * ho * wo, gn_groups, cpg).double()
@@ -151,6 +152,9 @@ TC_CASES = [
     dict(n=2, cins=[256], cout=256, h=32, w=32, k=3, pad=1, residual=True, sb_aff=True, sb_act=1),   # LFAE ResBlock conv2
     dict(n=1, cins=[64], cout=128, h=128, w=128, k=3, pad=1, f32_act=1),                    # LFAE down0
     dict(n=1, cins=[64], cout=64, h=64, w=64, k=3, pad=1),                                  # 64x64 (bw=64, bh=2)
+    dict(n=2, cins=[64], cout=768, h=16, w=16, k=1, pad=0, bias=False, f32_only=True),      # TMA-store epilogue (qkv)
+    dict(n=4, cins=[64], cout=64, h=8, w=8, k=3, pad=1, gn_groups=8, fps=2, f32_only=True), # TMA-store + GroupNorm sums
+    dict(n=2, cins=[128, 128], cout=128, h=16, w=16, k=3, pad=1, gn_groups=8, fps=1, f32_only=True),
 ]
 
 

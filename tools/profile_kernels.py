@@ -49,7 +49,9 @@ def conv_case(cin, cout, hw, k, gn=False, residual=False, srcs=1):
     stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=dev) if gn else None
 
     def run():
-        layer(a, nf, hw, hw, out_f32=out, residual=res, gn_stats=stats, gn_groups=8, rows_per_sample=F * hw * hw)
+        if stats is not None:
+            stats.zero_()
+        layer(a, nf, hw, hw, out_f32=out, residual=res, gn_stats=stats, gn_groups=8, rows_per_sample=F * hw * hw, stats_zeroed=True)
     flops = 2.0 * m * cout * cin * srcs * k * k
     byt = m * cin * srcs * 4 + m * cout * 4 * (2 if residual else 1)
     return run, flops, byt, lambda: layer.last_engine
