@@ -32,6 +32,8 @@ struct TcArgs {
     CUtensorMap tmB;
     CUtensorMap tmOut;               // fp32 [M][c_out], box {32 cols, 32 rows}, 128B swizzle (TMA-store epilogue)
     int32_t tma_store;
+    int32_t dbg;                     // LFDM_CONV_DBG ablation bits (timing experiments only): 1 no A loads, 2 no B loads, 4 no MMAs, 8 no stores
+    int32_t halo, halo_plane;        // 3x3 halo mode: tmA[src*4+1] = box {64, bw, bh+2}; bytes of one halo plane
     int32_t n_taps, tap_base;
     int8_t tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
     int32_t chunks[2];               // 64-channel chunks per source
@@ -166,13 +168,21 @@ __device__ __forceinline__ void epi_block32(const TcArgs& a, float* stage, const
     if (a.out_sb && a.sb_scale) sc4 = *reinterpret_cast<const float4*>(a.sb_scale + n);
     if (a.out_sb && a.sb_shift) sh4 = *reinterpret_cast<const float4*>(a.sb_shift + n);
     float gs = 0.f, gq = 0.f;
+    // all eight residual loads are issued before the first store: the output may alias the residual (in-place add), so
+    // the compiler cannot hoist them itself and the loop would otherwise pay eight serial global round trips
+    float4 res4[8];
+    if (a.residual) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            res4[i] = *reinterpret_cast<const float4*>(a.residual + (int64_t)rrow_l[i] * a.c_out + n);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rr = rsub + 4 * i;
         float4 v = reinterpret_cast<const float4*>(stage)[rr * 8 + (cq ^ (rr & 7))];
         v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
         if (a.residual) {
-            const float4 r4 = *reinterpret_cast<const float4*>(a.residual + (int64_t)rrow_l[i] * a.c_out + n);
+            const float4 r4 = res4[i];
             v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
         }
         if (a.gn_stats) {
@@ -224,11 +234,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     // [operand ring][8 x 4 KiB epilogue staging (1024-aligned: TMA-store / swizzle atoms)][barriers][GN accumulators]
+    // barrier block: operand ring (generic: STAGES stages; halo mode: the B ring, up to 6 stages), halo A ring (2), TMEM ring
+    constexpr int MAXB = 6;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 8 * 4096);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* empty_bar = full_bar + MAXB;
+    uint64_t* fullA_bar = empty_bar + MAXB;
+    uint64_t* emptyA_bar = fullA_bar + 2;
+    uint64_t* tfull_bar = emptyA_bar + 2;
     uint64_t* tempty_bar = tfull_bar + ACC;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + ACC);
+    // 3x3 halo mode (see the host side): the operand ring is re-cut into 2 A stages of 48 KiB -- one (bh+2)-row halo copy
+    // per horizontal tap offset dx, shared by the three vertical taps through the descriptor start address -- and a ring
+    // of NB single-tap weight stages.  A bytes per tile: 3 (bh+2)/bh tiles instead of 9.
+    constexpr int A_HALO_STAGE = 49152;
+    constexpr int NB = (STAGES * STAGE_BYTES - 2 * A_HALO_STAGE) / (2 * B_BYTES);
+    constexpr bool HALO_OK = WIDE && BN >= 64;
+    static_assert(!HALO_OK || (NB >= 3 && NB <= MAXB), "halo-mode weight ring");
+    const bool halo = HALO_OK && a.halo;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -239,7 +261,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         if (a.tma_store) ptx::prefetch_tensormap(&a.tmOut);
     }
     if (warp == 1 && ptx::elect_one()) {
-        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < MAXB; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&fullA_bar[i], 1); ptx::mbar_init(&emptyA_bar[i], 1); }
         for (int i = 0; i < ACC; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 128); }
         ptx::fence_barrier_init();
     }
@@ -261,7 +284,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (ptx::elect_one()) {
+        if (halo) {
+            if constexpr (HALO_OK) {
+                if (!(a.dbg & 2048) && ptx::elect_one()) {      // A producer: one halo copy per (dx, source, 64-channel chunk)
+                    int sa = 0; uint32_t pa = 0;
+                    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                        const int m_tile = tile / a.n_tiles;
+                        const int w_t = m_tile % a.tiles_w;
+                        const int h_t = (m_tile / a.tiles_w) % a.tiles_h;
+                        const int nf0 = m_tile / (a.tiles_w * a.tiles_h);
+                        const int w0 = w_t * a.bw, h0 = h_t * a.bh;
+                        for (int dxi = 0; dxi < 3; ++dxi)
+                            for (int src = 0; src < 2; ++src) {
+                                const CUtensorMap* tm = &a.tmA[src * 4 + 1];
+                                for (int ch = 0; ch < a.chunks[src]; ++ch) {
+                                    ptx::mbar_wait(&emptyA_bar[sa], pa ^ 1);
+                                    uint8_t* s = smem + sa * A_HALO_STAGE;
+                                    if (a.dbg & 1) { ptx::mbar_arrive_expect_tx(&fullA_bar[sa], 0); } else {
+                                    ptx::mbar_arrive_expect_tx(&fullA_bar[sa], 2 * a.halo_plane);
+                                    ptx::tma_load_5d(s, tm, &fullA_bar[sa], ch * BK, w0 + dxi - 1, h0 - 1, nf0, 0);
+                                    ptx::tma_load_5d(s + a.halo_plane, tm, &fullA_bar[sa], ch * BK, w0 + dxi - 1, h0 - 1, nf0, 1); }
+                                    if (++sa == 2) { sa = 0; pa ^= 1; }
+                                }
+                            }
+                    }
+                }
+            }
+        } else if (!(a.dbg & 2048) && ptx::elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
@@ -277,16 +326,91 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         for (int ch = 0; ch < a.chunks[src]; ++ch) {
                             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* s = smem + stage * STAGE_BYTES;
-                            ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                            ptx::mbar_arrive_expect_tx(&full_bar[stage], ((a.dbg & 1) ? 0 : 2 * A_BYTES) + ((a.dbg & 2) ? 0 : 2 * B_BYTES));
+                            if (!(a.dbg & 1)) {
                             ptx::tma_load_5d(s, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 0);
-                            ptx::tma_load_5d(s + A_BYTES, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 1);
+                            ptx::tma_load_5d(s + A_BYTES, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 1); }
+                            if (!(a.dbg & 2)) {
                             ptx::tma_load_4d(s + 2 * A_BYTES, &a.tmB, &full_bar[stage], kbase + ch * BK, n0,
                                              a.tap_base + tap, 0);
                             ptx::tma_load_4d(s + 2 * A_BYTES + B_BYTES, &a.tmB, &full_bar[stage], kbase + ch * BK, n0,
-                                             a.tap_base + tap, 1);
+                                             a.tap_base + tap, 1); }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== halo mode: weight (B) producer =====================
+        if constexpr (HALO_OK) {
+            if (halo && !(a.dbg & 2048) && ptx::elect_one()) {
+                int sb = 0; uint32_t pb = 0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int n0 = (tile % a.n_tiles) * BN;
+                    for (int dxi = 0; dxi < 3; ++dxi)
+                        for (int src = 0; src < 2; ++src) {
+                            const int kbase = src ? a.chunks[0] * BK : 0;
+                            for (int ch = 0; ch < a.chunks[src]; ++ch)
+                                for (int dyi = 0; dyi < 3; ++dyi) {
+                                    ptx::mbar_wait(&empty_bar[sb], pb ^ 1);
+                                    uint8_t* s = smem + 2 * A_HALO_STAGE + sb * (2 * B_BYTES);
+                                    if (a.dbg & 2) { ptx::mbar_arrive_expect_tx(&full_bar[sb], 0); } else {
+                                    ptx::mbar_arrive_expect_tx(&full_bar[sb], 2 * B_BYTES);
+                                    ptx::tma_load_4d(s, &a.tmB, &full_bar[sb], kbase + ch * BK, n0, a.tap_base + dyi * 3 + dxi, 0);
+                                    ptx::tma_load_4d(s + B_BYTES, &a.tmB, &full_bar[sb], kbase + ch * BK, n0, a.tap_base + dyi * 3 + dxi, 1); }
+                                    if (++sb == NB) { sb = 0; pb ^= 1; }
+                                }
+                        }
+                }
+            }
+        }
+    } else if (warp == 1 && halo) {
+        // ===================== halo mode: MMA issuer =====================
+        if constexpr (HALO_OK) {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int it = 0;
+            const int groups = 3 * kb_per_tap;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int as = it % ACC;
+                const uint32_t aphase = (it / ACC) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * DCOLS;
+                for (int g = 0; g < groups; ++g) {
+                    if (!(a.dbg & 2048)) ptx::mbar_wait(&fullA_bar[sa], pa);
+                    for (int dyi = 0; dyi < 3; ++dyi) {
+                        if (!(a.dbg & 2048)) ptx::mbar_wait(&full_bar[sb], pb);
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one()) {
+                            const uint32_t abase = ptx::smem_u32(smem + sa * A_HALO_STAGE) + (uint32_t)(dyi * a.bw * 128);
+                            const uint64_t da_hi = ptx::make_sw128_kmajor_desc(abase);
+                            const uint64_t da_lo = ptx::make_sw128_kmajor_desc(abase + (uint32_t)a.halo_plane);
+                            const uint64_t db_hi = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + 2 * A_HALO_STAGE + sb * (2 * B_BYTES)));
+#pragma unroll
+                            if (a.dbg & 64) {
+#pragma unroll
+                                for (int ks = 0; ks < BK / 16; ++ks)
+                                    ptx::umma_bf16(tmem_d, da_hi + (uint64_t)(ks * 2), db_hi + (uint64_t)(ks * 2), IDESC_WIDE, (g > 0 || dyi > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                                for (int ks = 0; ks < BK / 16; ++ks)
+                                    ptx::umma_bf16(tmem_d, da_lo + (uint64_t)(ks * 2), db_hi + (uint64_t)(ks * 2), IDESC, 1u);
+                            } else
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+                                if (a.dbg & 4) break;
+                                const uint64_t off = (uint64_t)(ks * 2);
+                                if (!(a.dbg & 32)) ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE, (g > 0 || dyi > 0 || ks > 0) ? 1u : 0u);
+                                if (!(a.dbg & 16)) ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, 1u);
+                            }
+                            if (!(a.dbg & 2048)) { ptx::umma_commit(&empty_bar[sb]);
+                            if (dyi == 2) ptx::umma_commit(&emptyA_bar[sa]); }
+                            if (dyi == 2 && g == groups - 1) ptx::umma_commit(&tfull_bar[as]);
+                        }
+                        __syncwarp();
+                        if (++sb == NB) { sb = 0; pb ^= 1; }
+                    }
+                    if (++sa == 2) { sa = 0; pa ^= 1; }
                 }
             }
         }
@@ -301,7 +425,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * DCOLS;
             for (int kb = 0; kb < n_kb; ++kb) {
-                ptx::mbar_wait(&full_bar[stage], phase);
+                if (!(a.dbg & 2048)) ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
                     const uint32_t sbase = ptx::smem_u32(smem + stage * STAGE_BYTES);
@@ -310,6 +434,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     const uint64_t db_hi = ptx::make_sw128_kmajor_desc(sbase + 2 * A_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
+                        if (a.dbg & 4) break;
                         const uint64_t off = (uint64_t)(ks * 2);   // 16 bf16 = 32 B, encoded >> 4
                         if constexpr (WIDE) {
                             ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE, (kb > 0 || ks > 0) ? 1u : 0u);  // [W_hi;W_lo]
@@ -321,7 +446,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC, 1u);
                         }
                     }
-                    ptx::umma_commit(&empty_bar[stage]);
+                    if (!(a.dbg & 2048)) ptx::umma_commit(&empty_bar[stage]);
                     if (kb == n_kb - 1) ptx::umma_commit(&tfull_bar[as]);
                 }
                 __syncwarp();
@@ -354,6 +479,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int as = it % ACC;
             const uint32_t aphase = (it / ACC) & 1;
+            if (a.dbg & 128) {
+                ptx::mbar_wait(&tfull_bar[as], aphase);
+                ptx::tc_fence_after();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tempty_bar[as]);
+                continue;
+            }
             const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
             const int w_t = m_tile % a.tiles_w;
             const int h_t = (m_tile / a.tiles_w) % a.tiles_h;
@@ -379,6 +511,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 orow_l[i] = (int32_t)oo; rrow_l[i] = (int32_t)rro;
             }
 
+            if (a.residual && vec_ok) {
+                // pull this warp's residual block (32 rows x BN columns) into L2 while the MMAs of the tile are in flight
+                const int pc = n0 + 32 * (lane & 7);
+                if (32 * (lane & 7) < BN && pc < a.c_out) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ptx::prefetch_l2(a.residual + (int64_t)rrow_l[i] * a.c_out + pc);
+                }
+            }
             ptx::mbar_wait(&tfull_bar[as], aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * DCOLS);
@@ -435,7 +575,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         for (int qd = 0; qd < 8; ++qd) st4[qd ^ sw] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
                         ptx::fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane == 0 && !(a.dbg & 8)) {
                             ptx::tma_store_2d(&a.tmOut, stage, nb, orow_l[0]);     // lane 0: orow_l[0] = first row of this warp's slab
                             ptx::tma_store_commit();
                         }
@@ -624,6 +764,29 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
             if (rc) return rc;
             a.tma_store = 1;
         }
+    }
+    // ---- 3x3 halo mode: tile inside one image, (bh+2) x bw halo copies per dx (A re-reads 9x -> 3(bh+2)/bh x)
+    a.halo = 0;
+    {
+        static const bool allow = (getenv("LFDM_CONV_NO_HALO") == nullptr);           // A/B switch
+        if (allow && d->mode == LFDM_CONV_DIRECT && d->stride == 1 && d->kh == 3 && d->kw == 3 && d->pad == 1 && bnf == 1 &&
+            bw >= 8 && bw <= 32 && (bn == 64 || bn == 128)) {
+            for (int s = 0; s < nsrc; ++s) {
+                const bf16* base = reinterpret_cast<const bf16*>(d->a_sb[s]);
+                const cuuint64_t C = (cuuint64_t)d->a_c[s], W = (cuuint64_t)d->w_in, H = (cuuint64_t)d->h_in;
+                cuuint64_t dims[5] = {C, W, H, (cuuint64_t)d->nf, 2};
+                cuuint64_t strides[4] = {C * 2, W * C * 2, H * W * C * 2, (cuuint64_t)d->a_plane[s] * 2};
+                cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)(bh + 2), 1, 1};
+                int rc = make_map(&a.tmA[s * 4 + 1], base, 5, dims, strides, box);
+                if (rc) return rc;
+            }
+            a.halo = 1;
+            a.halo_plane = (bh + 2) * bw * 128;
+        }
+    }
+    {
+        static const int dbg = getenv("LFDM_CONV_DBG") ? atoi(getenv("LFDM_CONV_DBG")) : 0;
+        a.dbg = dbg;
     }
     a.chunks[0] = d->a_c[0] / BK;
     a.chunks[1] = nsrc > 1 ? d->a_c[1] / BK : 0;

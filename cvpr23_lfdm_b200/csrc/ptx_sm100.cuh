@@ -86,6 +86,9 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, ui
 }
 
 // TMA store of a 2-D box from shared memory (bulk async group of the issuing thread)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(desc)),

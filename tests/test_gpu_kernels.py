@@ -155,6 +155,9 @@ TC_CASES = [
     dict(n=2, cins=[64], cout=768, h=16, w=16, k=1, pad=0, bias=False, f32_only=True),      # TMA-store epilogue (qkv)
     dict(n=4, cins=[64], cout=64, h=8, w=8, k=3, pad=1, gn_groups=8, fps=2, f32_only=True), # TMA-store + GroupNorm sums
     dict(n=2, cins=[128, 128], cout=128, h=16, w=16, k=3, pad=1, gn_groups=8, fps=1, f32_only=True),
+    dict(n=40, cins=[64], cout=64, h=32, w=32, k=3, pad=1, gn_groups=8, fps=20, f32_only=True),   # halo mode, 2-3 tiles per CTA
+    dict(n=3, cins=[64], cout=64, h=16, w=8, k=3, pad=1),                                         # halo mode, bw=8 bh=16
+    dict(n=2, cins=[64], cout=128, h=64, w=32, k=3, pad=1, residual=True),                        # halo mode, 16 row tiles
 ]
 
 

@@ -168,6 +168,7 @@ def main():
         for _ in range(args.iters):
             flush.fill_(0.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(1_000_000)      # park the GPU ~0.5 ms: the host enqueues the launch ahead, no launch gap inside the interval
             e0.record()
             run()
             e1.record()
