@@ -32,7 +32,7 @@ struct TcArgs {
     CUtensorMap tmB;
     CUtensorMap tmOut;               // fp32 [M][c_out], box {32 cols, 32 rows}, 128B swizzle (TMA-store epilogue)
     int32_t tma_store;
-    int32_t dbg;                     // LFDM_CONV_DBG ablation bits (timing experiments only): 1 no A loads, 2 no B loads, 4 no MMAs, 8 no stores
+    int32_t dbg;                     // LFDM_CONV_DBG ablation bits (timing experiments only): 1 no A loads, 2 no B loads, 8 no TMA stores, 128 no epilogue body
     int32_t halo, halo_plane;        // 3x3 halo mode: tmA[src*4+1] = box {64, bw, bh+2}; bytes of one halo plane
     int32_t n_taps, tap_base;
     int8_t tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // ===================== TMA producer =====================
         if (halo) {
             if constexpr (HALO_OK) {
-                if (!(a.dbg & 2048) && ptx::elect_one()) {      // A producer: one halo copy per (dx, source, 64-channel chunk)
+                if (ptx::elect_one()) {      // A producer: one halo copy per (dx, source, 64-channel chunk)
                     int sa = 0; uint32_t pa = 0;
                     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                         const int m_tile = tile / a.n_tiles;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     }
                 }
             }
-        } else if (!(a.dbg & 2048) && ptx::elect_one()) {
+        } else if (ptx::elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     } else if (warp == 3) {
         // ===================== halo mode: weight (B) producer =====================
         if constexpr (HALO_OK) {
-            if (halo && !(a.dbg & 2048) && ptx::elect_one()) {
+            if (halo && ptx::elect_one()) {
                 int sb = 0; uint32_t pb = 0;
                 for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                     const int n0 = (tile % a.n_tiles) * BN;
@@ -366,91 +366,92 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
         }
     } else if (warp == 1 && halo) {
-        // ===================== halo mode: MMA issuer =====================
+        // ===================== halo mode: MMA issuer (one elected thread runs the whole loop) =====================
         if constexpr (HALO_OK) {
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            if (ptx::elect_one()) {
+                constexpr uint64_t DB_STRIDE = (2 * B_BYTES) >> 4;
+                const uint64_t dA0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem));
+                const uint64_t dB0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + 2 * A_HALO_STAGE));
+                const uint64_t dy_step = (uint64_t)((a.bw * 128) >> 4), lo_step = (uint64_t)(a.halo_plane >> 4);
+                int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+                uint64_t dA = dA0, dB = dB0;
+                int it = 0;
+                const int groups = 3 * kb_per_tap;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                    const int as = it % ACC;
+                    const uint32_t aphase = (it / ACC) & 1;
+                    ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * DCOLS;
+                    uint32_t acc = 0u;
+                    for (int g = 0; g < groups; ++g) {
+                        ptx::mbar_wait(&fullA_bar[sa], pa);
+                        uint64_t da_hi = dA;
+#pragma unroll
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            ptx::mbar_wait(&full_bar[sb], pb);
+                            ptx::tc_fence_after();
+                            const uint64_t da_lo = da_hi + lo_step;
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+                                ptx::umma_bf16(tmem_d, da_hi + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_WIDE, acc);   // A_hi.[W_hi;W_lo]
+                                ptx::umma_bf16(tmem_d, da_lo + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC, 1u);          // + A_lo.W_hi
+                                acc = 1u;
+                            }
+                            ptx::umma_commit(&empty_bar[sb]);
+                            da_hi += dy_step;
+                            dB += DB_STRIDE;
+                            if (++sb == NB) { sb = 0; pb ^= 1; dB = dB0; }
+                        }
+                        ptx::umma_commit(&emptyA_bar[sa]);
+                        dA += (uint64_t)(A_HALO_STAGE >> 4);
+                        if (++sa == 2) { sa = 0; pa ^= 1; dA = dA0; }
+                    }
+                    ptx::umma_commit(&tfull_bar[as]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected thread runs the whole loop) =====================
+        // The tensor-core queue is short: whatever the issuing thread executes between the last MMA of one stage and the
+        // first of the next is exposed as tensor-pipe idle time (measured ~330 clk / stage with a per-stage elect + descriptor
+        // rebuild, i.e. as long as the 8 MMAs of a BN = 64 stage).  Descriptors are therefore carried incrementally.
+        if (ptx::elect_one()) {
+            constexpr uint64_t D_STRIDE = STAGE_BYTES >> 4, D_ALO = A_BYTES >> 4, D_B = (2 * A_BYTES) >> 4;
+            const uint64_t d0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem));
+            int stage = 0; uint32_t phase = 0;
+            uint64_t da_hi = d0;
             int it = 0;
-            const int groups = 3 * kb_per_tap;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int as = it % ACC;
                 const uint32_t aphase = (it / ACC) & 1;
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * DCOLS;
-                for (int g = 0; g < groups; ++g) {
-                    if (!(a.dbg & 2048)) ptx::mbar_wait(&fullA_bar[sa], pa);
-                    for (int dyi = 0; dyi < 3; ++dyi) {
-                        if (!(a.dbg & 2048)) ptx::mbar_wait(&full_bar[sb], pb);
-                        ptx::tc_fence_after();
-                        if (ptx::elect_one()) {
-                            const uint32_t abase = ptx::smem_u32(smem + sa * A_HALO_STAGE) + (uint32_t)(dyi * a.bw * 128);
-                            const uint64_t da_hi = ptx::make_sw128_kmajor_desc(abase);
-                            const uint64_t da_lo = ptx::make_sw128_kmajor_desc(abase + (uint32_t)a.halo_plane);
-                            const uint64_t db_hi = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + 2 * A_HALO_STAGE + sb * (2 * B_BYTES)));
-#pragma unroll
-                            if (a.dbg & 64) {
-#pragma unroll
-                                for (int ks = 0; ks < BK / 16; ++ks)
-                                    ptx::umma_bf16(tmem_d, da_hi + (uint64_t)(ks * 2), db_hi + (uint64_t)(ks * 2), IDESC_WIDE, (g > 0 || dyi > 0 || ks > 0) ? 1u : 0u);
-#pragma unroll
-                                for (int ks = 0; ks < BK / 16; ++ks)
-                                    ptx::umma_bf16(tmem_d, da_lo + (uint64_t)(ks * 2), db_hi + (uint64_t)(ks * 2), IDESC, 1u);
-                            } else
-#pragma unroll
-                            for (int ks = 0; ks < BK / 16; ++ks) {
-                                if (a.dbg & 4) break;
-                                const uint64_t off = (uint64_t)(ks * 2);
-                                if (!(a.dbg & 32)) ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE, (g > 0 || dyi > 0 || ks > 0) ? 1u : 0u);
-                                if (!(a.dbg & 16)) ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, 1u);
-                            }
-                            if (!(a.dbg & 2048)) { ptx::umma_commit(&empty_bar[sb]);
-                            if (dyi == 2) ptx::umma_commit(&emptyA_bar[sa]); }
-                            if (dyi == 2 && g == groups - 1) ptx::umma_commit(&tfull_bar[as]);
-                        }
-                        __syncwarp();
-                        if (++sb == NB) { sb = 0; pb ^= 1; }
-                    }
-                    if (++sa == 2) { sa = 0; pa ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        int stage = 0; uint32_t phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int as = it % ACC;
-            const uint32_t aphase = (it / ACC) & 1;
-            ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
-            ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * DCOLS;
-            for (int kb = 0; kb < n_kb; ++kb) {
-                if (!(a.dbg & 2048)) ptx::mbar_wait(&full_bar[stage], phase);
-                ptx::tc_fence_after();
-                if (ptx::elect_one()) {
-                    const uint32_t sbase = ptx::smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t da_hi = ptx::make_sw128_kmajor_desc(sbase);
-                    const uint64_t da_lo = ptx::make_sw128_kmajor_desc(sbase + A_BYTES);
-                    const uint64_t db_hi = ptx::make_sw128_kmajor_desc(sbase + 2 * A_BYTES);
+                uint32_t acc = 0u;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t da_lo = da_hi + D_ALO, db_hi = da_hi + D_B;
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
-                        if (a.dbg & 4) break;
                         const uint64_t off = (uint64_t)(ks * 2);   // 16 bf16 = 32 B, encoded >> 4
                         if constexpr (WIDE) {
-                            ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE, (kb > 0 || ks > 0) ? 1u : 0u);  // [W_hi;W_lo]
-                            ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, 1u);                                  // + A_lo.W_hi
+                            ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE, acc);      // A_hi.[W_hi;W_lo]
+                            ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, 1u);            // + A_lo.W_hi
                         } else {
                             const uint64_t db_lo = db_hi + (uint64_t)(B_BYTES >> 4);
-                            ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
+                            ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, acc);
                             ptx::umma_bf16(tmem_d, da_hi + off, db_lo + off, IDESC, 1u);
                             ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC, 1u);
                         }
+                        acc = 1u;
                     }
-                    if (!(a.dbg & 2048)) ptx::umma_commit(&empty_bar[stage]);
-                    if (kb == n_kb - 1) ptx::umma_commit(&tfull_bar[as]);
+                    ptx::umma_commit(&empty_bar[stage]);
+                    da_hi += D_STRIDE;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; da_hi = d0; }
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                ptx::umma_commit(&tfull_bar[as]);
             }
         }
     } else if (warp >= 4) {
