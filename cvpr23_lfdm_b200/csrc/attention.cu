@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restri
                                                            int64_t row_stride, const float* __restrict__ rot_cos,
                                                            const float* __restrict__ rot_sin,
                                                            const float* __restrict__ pos_bias, int warps_per_block) {
+    pdl_prologue_done();
     extern __shared__ __align__(16) float s_dyn[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int LP = CJ * 8;                 // padded sequence length (multiple of 8, >= L)
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(128, 3) attn_softmax_mma_kernel(const float* _
             for (int nt = 0; nt < 5; ++nt) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const float ex = expf(acc[mt][nt][2 * half + e] - mx);
+                    const float ex = __expf(acc[mt][nt][2 * half + e] - mx);   // ex2.approx: rel. error ~1e-6, inside the 1e-3 budget
                     acc[mt][nt][2 * half + e] = ex;
                     sum += ex;
                 }
@@ -454,6 +455,7 @@ __global__ void __launch_bounds__(128, 3) attn_softmax_mma16_kernel(const float*
                                                                     int64_t row_stride, const float* __restrict__ rot_cos,
                                                                     const float* __restrict__ rot_sin,
                                                                     const float* __restrict__ pos_bias) {
+    pdl_prologue_done();
     extern __shared__ __align__(16) float s_dyn[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* sq = s_dyn + (size_t)w * (2 * ML * QP2 + ML * VP2);    // Q [40][40] | K [40][40] | V [40][36]
@@ -542,6 +544,7 @@ __global__ void __launch_bounds__(128, 3) attn_softmax_mma16_kernel(const float*
     }
     // ---- bias + row softmax in registers (a row lives in the 4 lanes that share g)
     const float* pb = pos_bias ? pos_bias + (int64_t)h * L * L : nullptr;
+    const bool pair_ok = (L & 1) == 0 && (reinterpret_cast<uintptr_t>(pos_bias) & 7) == 0;
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt) {
 #pragma unroll
@@ -551,12 +554,16 @@ __global__ void __launch_bounds__(128, 3) attn_softmax_mma16_kernel(const float*
             float mx = -INFINITY;
 #pragma unroll
             for (int nt = 0; nt < 5; ++nt) {
+                const int j0 = 8 * nt + 2 * t;
+                float2 b2 = make_float2(0.f, 0.f);
+                if (pb && row_ok) {
+                    if (pair_ok) { if (j0 < L) b2 = *reinterpret_cast<const float2*>(pb + i * L + j0); }   // L even: (j0, j0+1) both < L
+                    else { if (j0 < L) b2.x = pb[i * L + j0]; if (j0 + 1 < L) b2.y = pb[i * L + j0 + 1]; }
+                }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int j = 8 * nt + 2 * t + e;
-                    float v = acc[mt][nt][2 * half + e];
-                    if (pb && row_ok && j < L) v += pb[i * L + j];
-                    v = (j < L) ? v : -INFINITY;
+                    float v = acc[mt][nt][2 * half + e] + (e ? b2.y : b2.x);
+                    v = (j0 + e < L) ? v : -INFINITY;
                     acc[mt][nt][2 * half + e] = v;
                     mx = fmaxf(mx, v);
                 }
@@ -568,7 +575,7 @@ __global__ void __launch_bounds__(128, 3) attn_softmax_mma16_kernel(const float*
             for (int nt = 0; nt < 5; ++nt) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const float ex = expf(acc[mt][nt][2 * half + e] - mx);
+                    const float ex = __expf(acc[mt][nt][2 * half + e] - mx);   // ex2.approx: rel. error ~1e-6, inside the 1e-3 budget
                     acc[mt][nt][2 * half + e] = ex;
                     sum += ex;
                 }
@@ -657,9 +664,11 @@ template <bool USE_MMA>
 __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
                                                                  int64_t out_plane, float* __restrict__ out_f32, int n_pos,
                                                                  int heads) {
+    pdl_prologue_done();
     extern __shared__ __align__(16) float s_dynl[];      // [LW][2 stages][2 tiles][32][TP]; aliased by the reduction
     __shared__ float s_red[LW][DH];
     __shared__ float s_max[DH];
+    __shared__ float s_rmax[LW][DH];                     // USE_MMA: per-warp running column maxima of k (online softmax)
     float (*s_ctxn)[DH + 4] = reinterpret_cast<float (*)[DH + 4]>(s_dynl + LW * DH * DH);   // aliases tiles (after phase 2)
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a = lane >> 3, b = lane & 7;
@@ -671,20 +680,25 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
     const float scale = 0.17677669529663687f;
     float* wbuf = s_dynl + w * 4 * TILE;                  // stage s: k/q tile at wbuf + s*2*TILE, v tile at + TILE
 
-    // phase 1: column max of k over positions (lane = d)
-    float mx = -INFINITY;
+    // phase 1 (CUDA-core variant only): column max of k over positions (lane = d).  The tensor-core variant keeps a running
+    // maximum per warp instead (online softmax: accumulators are rescaled when the maximum moves), which saves this whole
+    // extra pass over k (a quarter of the kernel's DRAM reads) and its exposed latency.
+    float kmax = -INFINITY;
+    if constexpr (!USE_MMA) {
+        float mx = -INFINITY;
 #pragma unroll 16
-    for (int n = w; n < n_pos; n += LW) mx = fmaxf(mx, base[(int64_t)n * ld + hid + lane]);
-    s_red[w][lane] = mx;
-    __syncthreads();
-    if (w == 0) {
-        float m = s_red[0][lane];
+        for (int n = w; n < n_pos; n += LW) mx = fmaxf(mx, base[(int64_t)n * ld + hid + lane]);
+        s_red[w][lane] = mx;
+        __syncthreads();
+        if (w == 0) {
+            float m = s_red[0][lane];
 #pragma unroll
-        for (int i = 1; i < LW; ++i) m = fmaxf(m, s_red[i][lane]);
-        s_max[lane] = m;
+            for (int i = 1; i < LW; ++i) m = fmaxf(m, s_red[i][lane]);
+            s_max[lane] = m;
+        }
+        __syncthreads();
+        kmax = s_max[lane];
     }
-    __syncthreads();
-    const float kmax = s_max[lane];
 
     // phase 2: ctx[d][e] += exp(k[n][d] - max_d) * v[n][e];  den[d] += exp(..)
     float ctx[8][4];
@@ -719,14 +733,32 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
         float* kt = wbuf + st * 2 * TILE;
         const float* vt = kt + TILE;
         const int n0 = c * 32;
+        const int rows = min(32, n_pos - n0);
+        if constexpr (USE_MMA) {
+            float cm = -INFINITY;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) cm = fmaxf(cm, (r < rows) ? kt[r * TP + lane] : -INFINITY);
+            const float nm = fmaxf(kmax, cm);
+            const float f = __expf(kmax - nm);            // first chunk: exp(-inf) = 0 on all-zero accumulators
+            kmax = nm;
+            den *= f;
+            const int g = lane >> 2;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float f0 = __shfl_sync(0xffffffffu, f, g + 16 * mt), f1 = __shfl_sync(0xffffffffu, f, g + 16 * mt + 8);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    cacc[mt][nt][0] *= f0; cacc[mt][nt][1] *= f0; cacc[mt][nt][2] *= f1; cacc[mt][nt][3] *= f1;
+                }
+            }
+        }
 #pragma unroll 8
         for (int r = 0; r < 32; ++r) {
-            const float e = (n0 + r < n_pos) ? expf(kt[r * TP + lane] - kmax) : 0.f;
+            const float e = (r < rows) ? __expf(kt[r * TP + lane] - kmax) : 0.f;
             den += e;
             kt[r * TP + lane] = e;
         }
         __syncwarp();
-        const int rows = min(32, n_pos - n0);
         if constexpr (USE_MMA) {
             // ctx (32 x 32) += ek^T (32 x 32 rows) . v : split-bf16 mma.m16n8k16, A(m = d, k = n) = ek[n][d], B(k = n, n = e) = v[n][e]
             float* vtw = const_cast<float*>(vt);
@@ -789,12 +821,25 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
             *reinterpret_cast<float4*>(s_ctx + (w * DH + 8 * a + i) * DH + 4 * b) = make_float4(ctx[i][0], ctx[i][1], ctx[i][2], ctx[i][3]);
     }
     s_red[w][lane] = den;
+    s_rmax[w][lane] = kmax;
     __syncthreads();
     for (int i = threadIdx.x; i < DH * DH; i += 32 * LW) {
         const int d = i / DH, e = i % DH;
         float acc = 0.f, dd = 0.f;
+        if constexpr (USE_MMA) {                         // warps hold sums relative to their own maxima: bring them to the common one
+            float m = s_rmax[0][d];
 #pragma unroll
-        for (int ww = 0; ww < LW; ++ww) { acc += s_ctx[(ww * DH + d) * DH + e]; dd += s_red[ww][d]; }
+            for (int ww = 1; ww < LW; ++ww) m = fmaxf(m, s_rmax[ww][d]);
+#pragma unroll
+            for (int ww = 0; ww < LW; ++ww) {
+                const float sc = __expf(s_rmax[ww][d] - m);          // a warp without chunks: exp(-inf) = 0
+                acc = fmaf(s_ctx[(ww * DH + d) * DH + e], sc, acc);
+                dd = fmaf(s_red[ww][d], sc, dd);
+            }
+        } else {
+#pragma unroll
+            for (int ww = 0; ww < LW; ++ww) { acc += s_ctx[(ww * DH + d) * DH + e]; dd += s_red[ww][d]; }
+        }
         s_ctxn[d][e] = acc / dd;                         // softmax normalisation of k folded into the context
     }
     __syncthreads();
@@ -841,7 +886,7 @@ __global__ void __launch_bounds__(32 * LW, 3) attn_linear_kernel(const float* __
             float sum = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                x[i].x = expf(x[i].x - m); x[i].y = expf(x[i].y - m); x[i].z = expf(x[i].z - m); x[i].w = expf(x[i].w - m);
+                x[i].x = __expf(x[i].x - m); x[i].y = __expf(x[i].y - m); x[i].z = __expf(x[i].z - m); x[i].w = __expf(x[i].w - m);
                 sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
             }
             const float inv = scale / sum;
@@ -944,10 +989,9 @@ static int launch_attn_softmax(const float* qkv, void* out_sb, int64_t out_plane
     }
     const int64_t units = n_seq * heads;
     const int64_t blocks = (units + wpb - 1) / wpb;
-    attn_softmax_kernel<RIP, CJ, ALIAS_P><<<(unsigned)blocks, 32 * wpb, per_warp * wpb, st>>>(
-        qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride, row_stride,
-        rot_cos, rot_sin, pos_bias, wpb);
-    LFDM_CHECK_LAUNCH();
+    LFDM_LAUNCH_PDL((attn_softmax_kernel<RIP, CJ, ALIAS_P>), dim3((unsigned)blocks), dim3(32 * wpb), per_warp * wpb, st,
+                    qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride, row_stride,
+                    rot_cos, rot_sin, pos_bias, wpb);
     return 0;
 }
 
@@ -972,10 +1016,9 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
                 attr16 = true;
             }
             const int64_t units = n_seq * heads;
-            attn_softmax_mma16_kernel<<<(unsigned)((units + 3) / 4), 128, smem, st>>>(
-                qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride, row_stride,
-                rot_cos, rot_sin, pos_bias);
-            LFDM_CHECK_LAUNCH();
+            LFDM_LAUNCH_PDL(attn_softmax_mma16_kernel, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
+                            qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
+                            row_stride, rot_cos, rot_sin, pos_bias);
             return 0;
         }
         if (use_mma) {
@@ -1012,11 +1055,10 @@ extern "C" int lfdm_attn_linear(const float* qkv, void* out_sb, int64_t out_plan
     }
     static const bool use_mma = (getenv("LFDM_ATTN_SIMT") == nullptr);          // A/B switch: CUDA-core tiling instead
     if (use_mma)
-        attn_linear_kernel<true><<<(unsigned)(n_frames * heads), 32 * LW, smem, (cudaStream_t)stream>>>(
-            qkv, (bf16*)out_sb, out_plane, out_f32, n_pos, heads);
+        LFDM_LAUNCH_PDL(attn_linear_kernel<true>, dim3((unsigned)(n_frames * heads)), dim3(32 * LW), smem, (cudaStream_t)stream,
+                        qkv, (bf16*)out_sb, out_plane, out_f32, n_pos, heads);
     else
-        attn_linear_kernel<false><<<(unsigned)(n_frames * heads), 32 * LW, smem, (cudaStream_t)stream>>>(
-            qkv, (bf16*)out_sb, out_plane, out_f32, n_pos, heads);
-    LFDM_CHECK_LAUNCH();
+        LFDM_LAUNCH_PDL(attn_linear_kernel<false>, dim3((unsigned)(n_frames * heads)), dim3(32 * LW), smem, (cudaStream_t)stream,
+                        qkv, (bf16*)out_sb, out_plane, out_f32, n_pos, heads);
     return 0;
 }

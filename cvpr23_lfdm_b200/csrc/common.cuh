@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <cstdlib>
+#include <cstring>
+#include <utility>
 #include "../../include/lfdm_b200.h"
 
 typedef __nv_bfloat16 bf16;
@@ -10,6 +13,40 @@ typedef __nv_bfloat16 bf16;
 #define LFDM_CHECK_LAUNCH()                                   \
     do {                                                      \
         cudaError_t e__ = cudaPeekAtLastError();              \
+        if (e__ != cudaSuccess) return (int)e__;              \
+    } while (0)
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// One sampling step is ~180 back-to-back launches of short kernels on one stream.  Kernels launched through
+// lfdm_launch_pdl() carry the programmatic-stream-serialization attribute (also inside a captured CUDA graph): their
+// CTAs may become resident and run their prologue (barrier init, TMEM allocation, index math) while the previous kernel
+// drains.  Contract: such a kernel calls pdl_prologue_done() (or pdl_trigger() ... pdl_wait()) before its first global
+// memory access - griddepcontrol.wait returns only when the preceding grid has completed and its writes are visible.
+// LFDM_NO_PDL=1 turns the attribute off (the device-side instructions are then no-ops).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue_done() { pdl_trigger(); pdl_wait(); }
+
+inline bool lfdm_pdl_enabled() {
+    static const bool on = (getenv("LFDM_NO_PDL") == nullptr);
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t lfdm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    memset(at, 0, sizeof(at));
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = lfdm_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+#define LFDM_LAUNCH_PDL(...)                                   \
+    do {                                                      \
+        cudaError_t e__ = lfdm_launch_pdl(__VA_ARGS__);       \
         if (e__ != cudaSuccess) return (int)e__;              \
     } while (0)
 

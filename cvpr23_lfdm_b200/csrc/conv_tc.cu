@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
+    pdl_trigger();       // PDL: the next kernel's CTAs may become resident as SMs free up; everything up to pdl_wait() below
+                         // (barrier init, TMEM allocation, tensor-map prefetch) overlaps the previous kernel's tail
     if (warp == 0 && ptx::elect_one()) {
         for (int i = 0; i < 8; ++i) ptx::prefetch_tensormap(&a.tmA[i]);
         ptx::prefetch_tensormap(&a.tmB);
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();          // the producing kernel has completed: activations / residual / GroupNorm accumulators are safe to touch
 
     const int kb_per_tap = a.chunks[0] + a.chunks[1];
     const int n_kb = a.n_taps * kb_per_tap;
@@ -664,8 +667,7 @@ int launch(const TcArgs& a, cudaStream_t st) {
     }
     int total = a.m_tiles * a.n_tiles;
     int grid = total < num_sms ? total : num_sms;
-    conv_tc_kernel<BN, STAGES, WIDE><<<grid, NUM_THREADS, SMEM, st>>>(a);
-    LFDM_CHECK_LAUNCH();
+    LFDM_LAUNCH_PDL((conv_tc_kernel<BN, STAGES, WIDE>), dim3(grid), dim3(NUM_THREADS), (size_t)SMEM, st, a);
     return 0;
 }
 

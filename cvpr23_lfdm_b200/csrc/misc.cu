@@ -50,6 +50,7 @@ __global__ void sinusoidal_kernel(const int64_t* __restrict__ t, const float* __
 
 __global__ void ss_combine_kernel(const float* __restrict__ time_tab, const int32_t* __restrict__ step_idx,
                                   const float* __restrict__ cond_tab, float* __restrict__ ss, int b, int n) {
+    pdl_prologue_done();
     const int row = step_idx ? *step_idx : 0;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b * n) return;
@@ -61,6 +62,7 @@ __global__ void ss_combine_kernel(const float* __restrict__ time_tab, const int3
 __global__ void __launch_bounds__(256) to_rows_kernel(const float* __restrict__ in, int c, int f, int p, int64_t sb,
                                                       int64_t sc, int64_t sf, int c_pad, bf16* __restrict__ out_sb,
                                                       int64_t out_plane, float* __restrict__ out_f32) {
+    pdl_prologue_done();
     __shared__ float tile[32][33];
     const int n = blockIdx.z, bi = n / f, fi = n % f;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(256) to_rows_kernel(const float* __restrict__ 
 // rows[(b*F+f)*P+p][ld] -> out[b][c][f][p]
 __global__ void __launch_bounds__(256) from_rows_kernel(const float* __restrict__ rows, int ld, int c, int f, int p,
                                                         float* __restrict__ out) {
+    pdl_prologue_done();
     __shared__ float tile[32][33];
     const int n = blockIdx.z, bi = n / f, fi = n % f;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -140,6 +143,52 @@ __global__ void __launch_bounds__(256) im2col_small_kernel(const float* __restri
     }
 }
 
+// Same result, one CTA per output image row: the c x ks x (w + 2 pad) input patch is staged (zero padded) in shared
+// memory, every thread owns one 4-wide k group (its four (channel, tap) smem offsets are computed once) and walks the
+// pixels of the row; stores are 8-byte, contiguous across the threads of a pixel.  (The gather straight from global
+// memory above touches ~100 cache lines per warp load.)
+__global__ void __launch_bounds__(256) im2col_row_kernel(const float* __restrict__ in, int c, int f, int h, int w, int ks,
+                                                         int pad, int k_pad, bf16* __restrict__ out_sb, int64_t out_plane) {
+    pdl_prologue_done();
+    extern __shared__ float patch[];                      // [c][ks][w + 2 pad]
+    const int wp = w + 2 * pad;
+    const int row = blockIdx.x;                           // (n, y)
+    const int n = row / h, y = row - n * h;
+    const int bi = n / f, fi = n - bi * f;
+    const int hw = h * w;
+    const float* base = in + ((int64_t)bi * c * f + fi) * hw;
+    for (int i = threadIdx.x; i < c * ks * wp; i += blockDim.x) {
+        const int xx = i % wp - pad, r = i / wp;
+        const int kh = r % ks, ch = r / ks;
+        const int yy = y - pad + kh;
+        float v = 0.f;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = base[(int64_t)ch * f * hw + yy * w + xx];
+        patch[i] = v;
+    }
+    __syncthreads();
+    const int kq_per_row = k_pad >> 2, kreal = ks * ks * c;
+    const int kq = threadIdx.x % kq_per_row, px0 = threadIdx.x / kq_per_row, pstep = blockDim.x / kq_per_row;
+    int off[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int k = kq * 4 + e;
+        off[e] = -1;
+        if (k < kreal) {
+            const int tap = k / c, ch = k - tap * c;
+            const int kh = tap / ks, kw = tap - kh * ks;
+            off[e] = (ch * ks + kh) * wp + kw;
+        }
+    }
+    for (int px = px0; px < w; px += pstep) {
+        float4 v;
+        v.x = off[0] >= 0 ? patch[off[0] + px] : 0.f;
+        v.y = off[1] >= 0 ? patch[off[1] + px] : 0.f;
+        v.z = off[2] >= 0 ? patch[off[2] + px] : 0.f;
+        v.w = off[3] >= 0 ? patch[off[3] + px] : 0.f;
+        store_sb4(out_sb, out_plane, ((int64_t)row * w + px) * k_pad + kq * 4, v);
+    }
+}
+
 __global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__ in, int h, int w, int c,
                                                        float* __restrict__ out_f32, bf16* __restrict__ out_sb,
                                                        int64_t out_plane, int64_t total) {
@@ -189,6 +238,65 @@ __global__ void __launch_bounds__(256) unet_heads_kernel(const float* __restrict
     }
 }
 
+// c == 64, na + no <= 4: eight lanes per row (two float4 each -> every warp load instruction covers four full rows =
+// four 256-byte segments), weights held in registers, three shuffles per output channel.
+__global__ void __launch_bounds__(256) unet_heads64_kernel(const float* __restrict__ a, const float* __restrict__ wa,
+                                                           const float* __restrict__ ba, int na,
+                                                           const float* __restrict__ o, const float* __restrict__ wo,
+                                                           const float* __restrict__ bo, int no, int f, int p,
+                                                           int64_t m_total, float* __restrict__ out) {
+    pdl_prologue_done();
+    const int lane = threadIdx.x & 31, sub = lane & 7, rsel = lane >> 3;
+    const int nch = na + no;
+    float w[4][8], bias[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        bias[ch] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[ch][j] = 0.f;
+        if (ch < nch) {
+            const float* wv = ch < na ? wa + ch * 64 : wo + (ch - na) * 64;
+            const float4 w0 = *reinterpret_cast<const float4*>(wv + sub * 8), w1 = *reinterpret_cast<const float4*>(wv + sub * 8 + 4);
+            w[ch][0] = w0.x; w[ch][1] = w0.y; w[ch][2] = w0.z; w[ch][3] = w0.w;
+            w[ch][4] = w1.x; w[ch][5] = w1.y; w[ch][6] = w1.z; w[ch][7] = w1.w;
+            bias[ch] = ch < na ? (ba ? ba[ch] : 0.f) : (bo ? bo[ch - na] : 0.f);
+        }
+    }
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t m0 = gw * 4; m0 < m_total; m0 += nw * 4) {
+        const int64_t m = m0 + rsel;
+        if (m >= m_total) continue;        // whole 8-lane groups drop out together (shuffles below stay inside a group)
+        const float4 a0 = *reinterpret_cast<const float4*>(a + m * 64 + sub * 8), a1 = *reinterpret_cast<const float4*>(a + m * 64 + sub * 8 + 4);
+        const float4 o0 = *reinterpret_cast<const float4*>(o + m * 64 + sub * 8), o1 = *reinterpret_cast<const float4*>(o + m * 64 + sub * 8 + 4);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        float acc[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            acc[ch] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[ch] = fmaf(ch < na ? av[j] : ov[j], w[ch][j], acc[ch]);
+        }
+        const unsigned gmask = 0xffu << (rsel * 8);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            acc[ch] += __shfl_xor_sync(gmask, acc[ch], 1);
+            acc[ch] += __shfl_xor_sync(gmask, acc[ch], 2);
+            acc[ch] += __shfl_xor_sync(gmask, acc[ch], 4);
+        }
+        if (sub < nch) {
+            const int64_t n = m / p;
+            const int pp = (int)(m - n * p);
+            const int bi = (int)(n / f), fi = (int)(n - (int64_t)bi * f);
+            float v = acc[0] + bias[0];
+            if (sub == 1) v = acc[1] + bias[1];
+            if (sub == 2) v = acc[2] + bias[2];
+            if (sub == 3) v = acc[3] + bias[3];
+            out[(((int64_t)bi * nch + sub) * f + fi) * p + pp] = v;
+        }
+    }
+}
+
 __global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t plane, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         store_sb1(out, plane, i, in[i]);
@@ -228,7 +336,7 @@ extern "C" int lfdm_ss_combine(const float* time_tab, const int32_t* step_idx, c
                                int n, void* stream) {
     if (!time_tab || !cond_tab || !ss) return LFDM_E_BADARG;
     int total = b * n;
-    ss_combine_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(time_tab, step_idx, cond_tab, ss, b, n);
+    LFDM_LAUNCH_PDL(ss_combine_kernel, dim3((total + 255) / 256), dim3(256), 0, (cudaStream_t)stream, time_tab, step_idx, cond_tab, ss, b, n);
     LFDM_CHECK_LAUNCH();
     return 0;
 }
@@ -237,7 +345,7 @@ extern "C" int lfdm_to_rows(const float* in, int b, int c, int f, int p, int64_t
                             void* out_sb, int64_t out_plane, float* out_f32, void* stream) {
     if (!in || c_pad < c || (!out_sb && !out_f32)) return LFDM_E_BADARG;
     dim3 grid((p + 31) / 32, (c_pad + 31) / 32, b * f);
-    to_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, c, f, p, sb, sc, sf, c_pad, (bf16*)out_sb, out_plane, out_f32);
+    LFDM_LAUNCH_PDL(to_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, in, c, f, p, sb, sc, sf, c_pad, (bf16*)out_sb, out_plane, out_f32);
     LFDM_CHECK_LAUNCH();
     return 0;
 }
@@ -245,7 +353,7 @@ extern "C" int lfdm_to_rows(const float* in, int b, int c, int f, int p, int64_t
 extern "C" int lfdm_from_rows(const float* rows, int ld, int b, int c, int f, int p, float* out, void* stream) {
     if (!rows || !out || ld < c) return LFDM_E_BADARG;
     dim3 grid((p + 31) / 32, (c + 31) / 32, b * f);
-    from_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, ld, c, f, p, out);
+    LFDM_LAUNCH_PDL(from_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, rows, ld, c, f, p, out);
     LFDM_CHECK_LAUNCH();
     return 0;
 }
@@ -255,6 +363,13 @@ extern "C" int lfdm_im2col_small(const float* in, int b, int c, int f, int h, in
     if (!in || !out_sb || k_pad < ksize * ksize * c || (k_pad & 3)) return LFDM_E_BADARG;
     if ((int64_t)b * f * h * w >= (1ll << 31)) return LFDM_E_BADARG;
     int64_t total4 = (int64_t)b * f * h * w * (k_pad >> 2);
+    const int kq_per_row = k_pad >> 2;
+    const size_t patch_bytes = (size_t)c * ksize * (w + 2 * pad) * sizeof(float);
+    if (kq_per_row <= 256 && patch_bytes <= 40 * 1024) {
+        const int pstep = 256 / kq_per_row;
+        LFDM_LAUNCH_PDL(im2col_row_kernel, dim3((unsigned)(b * f * h)), dim3(pstep * kq_per_row), patch_bytes, (cudaStream_t)stream,
+                        in, c, f, h, w, ksize, pad, k_pad, (bf16*)out_sb, out_plane);
+    } else
     im2col_small_kernel<<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(in, c, f, h, w, ksize, pad, k_pad,
                                                                          (bf16*)out_sb, out_plane, total4);
     LFDM_CHECK_LAUNCH();
@@ -277,6 +392,12 @@ extern "C" int lfdm_unet_heads(const float* a, const float* wa, const float* ba,
     int64_t m = (int64_t)b * f * p;
     int64_t blocks = (m + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    if (c == 64 && na + no <= 4 && na >= 0 && no >= 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(o) |
+                                                         reinterpret_cast<uintptr_t>(wa) | reinterpret_cast<uintptr_t>(wo)) & 15) == 0) {
+        int64_t b4 = (m + 31) / 32;            // 8 warps x 4 rows per pass
+        if (b4 > 148 * 8) b4 = 148 * 8;
+        LFDM_LAUNCH_PDL(unet_heads64_kernel, dim3((unsigned)b4), dim3(256), 0, (cudaStream_t)stream, a, wa, ba, na, o, wo, bo, no, f, p, m, out);
+    } else
     unet_heads_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, wa, ba, na, o, wo, bo, no, c, f, p, m, out);
     LFDM_CHECK_LAUNCH();
     return 0;

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        float* __restrict__ out_f32, bf16* __restrict__ out_sb,
                                                        int64_t out_plane, int64_t m, int c, int cpg, int groups,
                                                        int64_t rows_per_sample, float eps, int64_t ss_stride) {
+    pdl_prologue_done();
     extern __shared__ float2 s_mr[];   // (mean, rstd) per (b, g)
     const int c4 = c >> 2;
     const int64_t total = m * c4;
@@ -105,6 +106,7 @@ template <int G, int NJ>      // G lanes per row (G <= 32), NJ float4 per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         bf16* __restrict__ out_sb, int64_t out_plane,
                                                         float* __restrict__ out_f32, int64_t m, int c, float eps) {
+    pdl_prologue_done();
     constexpr int RPW = 32 / G;                 // rows per warp per pass
     constexpr int PASSES = (NJ >= 4) ? 1 : (4 / NJ);   // independent row passes kept in flight
     const int lane = threadIdx.x & 31;
@@ -194,10 +196,8 @@ extern "C" int lfdm_gn_apply(const float* x, const double* stats, const float* g
     if (blocks > 148 * 16) blocks = 148 * 16;
     size_t smem = sizeof(float2) * (size_t)(m / rows_per_sample) * groups;
     if (smem > 40000) return LFDM_E_UNSUPP;
-    gn_apply_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(x, stats, gamma, beta, ss, residual, out_f32,
-                                                             (bf16*)out_sb, out_plane, m, c, c / groups, groups,
-                                                             rows_per_sample, eps, ss_stride);
-    LFDM_CHECK_LAUNCH();
+    LFDM_LAUNCH_PDL(gn_apply_kernel, dim3(blocks), dim3(256), smem, (cudaStream_t)stream, x, stats, gamma, beta, ss, residual,
+                    out_f32, (bf16*)out_sb, out_plane, m, c, c / groups, groups, rows_per_sample, eps, ss_stride);
     return 0;
 }
 
@@ -212,7 +212,8 @@ extern "C" int lfdm_layernorm(const float* x, const float* gamma, void* out_sb, 
         rows_per_block = 8 * (32 / G) * ((NJ >= 4) ? 1 : (4 / NJ));                                                   \
         int64_t blocks = (m + rows_per_block - 1) / rows_per_block;                                                   \
         if (blocks > 148 * 16) blocks = 148 * 16;                                                                     \
-        layernorm_kernel<G, NJ><<<(int)blocks, 256, 0, st>>>(x, gamma, (bf16*)out_sb, out_plane, out_f32, m, c, eps);  \
+        LFDM_LAUNCH_PDL((layernorm_kernel<G, NJ>), dim3((unsigned)blocks), dim3(256), 0, st, x, gamma, (bf16*)out_sb,   \
+                        out_plane, out_f32, m, c, eps);                                                               \
     } while (0)
     if (c4 <= 4) LFDM_LN_LAUNCH(4, 1);
     else if (c4 <= 8) LFDM_LN_LAUNCH(8, 1);

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) x0_abs_kernel(const float* __restrict__ x
                                                      const float* __restrict__ coef,
                                                      const int32_t* __restrict__ step_idx, float* __restrict__ absx0,
                                                      int64_t total4) {
+    pdl_prologue_done();
     const int row = step_idx ? *step_idx : 0;
     const float c1 = coef[row * 8 + 0], c2 = coef[row * 8 + 1];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256) x0_abs_kernel(const float* __restrict__ x
 // min pass; one 1024-thread block per sample.  Non-negative IEEE floats order like their uint32 bit patterns.
 __global__ void __launch_bounds__(1024) quantile_kernel(const float* __restrict__ absx0, float* __restrict__ s_out,
                                                         int64_t n, int64_t k_lo, float w_hi) {
+    pdl_prologue_done();
     __shared__ unsigned int hist[256];
     __shared__ unsigned int sh_prefix, sh_k, sh_ceq;
     __shared__ unsigned int sh_min[32];
@@ -101,6 +103,7 @@ __global__ void __launch_bounds__(256) update_kernel(const float* __restrict__ x
                                                      const int32_t* __restrict__ step_idx, float* __restrict__ x_out,
                                                      float* __restrict__ x0_out, int64_t n4_per_sample,
                                                      int64_t total4) {
+    pdl_prologue_done();
     const int row = step_idx ? *step_idx : 0;
     const float* cf = coef + row * 8;
     const float c1 = cf[0], c2 = cf[1], ca = cf[2], cb = cf[3], sg = cf[4], ce = cf[5];
@@ -129,7 +132,10 @@ __global__ void __launch_bounds__(256) update_kernel(const float* __restrict__ x
     }
 }
 
-__global__ void advance_kernel(int32_t* step_idx) { *step_idx += 1; }
+__global__ void advance_kernel(int32_t* step_idx) {
+    pdl_prologue_done();
+    *step_idx += 1;
+}
 
 }  // namespace
 
@@ -139,7 +145,7 @@ extern "C" int lfdm_sampler_x0(const float* x, const float* eps, const float* co
     int64_t total4 = n_per_sample / 4 * b;
     int blocks = (int)((total4 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    x0_abs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, eps, coef, step_idx, absx0, total4);
+    LFDM_LAUNCH_PDL(x0_abs_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, eps, coef, step_idx, absx0, total4);
     LFDM_CHECK_LAUNCH();
     return 0;
 }
@@ -148,7 +154,7 @@ extern "C" int lfdm_sampler_quantile(const float* absx0, float* s, int64_t n_per
                                      float w_hi, void* workspace, void* stream) {
     (void)workspace;
     if (!absx0 || !s || k_lo < 0 || k_lo >= n_per_sample) return LFDM_E_BADARG;
-    quantile_kernel<<<b, 1024, 0, (cudaStream_t)stream>>>(absx0, s, n_per_sample, k_lo, w_hi);
+    LFDM_LAUNCH_PDL(quantile_kernel, dim3(b), dim3(1024), 0, (cudaStream_t)stream, absx0, s, n_per_sample, k_lo, w_hi);
     LFDM_CHECK_LAUNCH();
     return 0;
 }
@@ -160,11 +166,11 @@ extern "C" int lfdm_sampler_update(const float* x, const float* eps, const float
     int64_t total4 = n_per_sample / 4 * b;
     int blocks = (int)((total4 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, eps, noise, s, coef, step_idx, x_out, x0_out,
-                                                           n_per_sample / 4, total4);
+    LFDM_LAUNCH_PDL(update_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, eps, noise, s, coef, step_idx, x_out,
+                    x0_out, n_per_sample / 4, total4);
     LFDM_CHECK_LAUNCH();
     if (advance && step_idx) {
-        advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_idx);
+        LFDM_LAUNCH_PDL(advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_idx);
         LFDM_CHECK_LAUNCH();
     }
     return 0;

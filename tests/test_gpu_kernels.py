@@ -270,13 +270,15 @@ def test_attn_softmax_lengths(L):
     close(out, ref, f"softmax attention L={L}")
 
 
-@pytest.mark.parametrize("n_pos", [16, 64, 1024])
+@pytest.mark.parametrize("n_pos", [16, 50, 64, 1024])
 def test_attn_linear(n_pos):
     from cvpr23_lfdm_b200.engine import ops
     g = torch.Generator().manual_seed(4)
     nf, heads = 3, 2
     hid = heads * 32
     qkv = torch.randn(nf, n_pos, 3 * hid, generator=g) * 1.5
+    # a rising trend on k: the running column maximum of the single-pass (online softmax) kernel moves in every chunk
+    qkv[:, :, hid:2 * hid] += torch.linspace(-6.0, 6.0, n_pos)[None, :, None]
     q, k, v = [t.reshape(nf, n_pos, heads, 32).permute(0, 2, 3, 1) for t in qkv.chunk(3, -1)]    # (nf, h, d, n)
     q = q.softmax(dim=-2) * 32 ** -0.5
     k = k.softmax(dim=-1)
@@ -467,3 +469,12 @@ def test_layout_kernels():
                                 stream()), "heads")
     ref = torch.cat([F.linear(a, wa, ba), F.linear(o, wo, bo)], 1).reshape(2, 3, 16, 3).permute(0, 3, 1, 2).reshape(2, 3, 3, 4, 4)
     close(outh, ref, "heads", rtol=1e-4, atol=1e-5)
+    # heads, c = 64 fast path (eight lanes per row), ragged row count (45 rows: last group of four is partial)
+    a, o = torch.randn(3 * 15, 64, generator=g), torch.randn(3 * 15, 64, generator=g)
+    wa, ba, wo, bo = torch.randn(2, 64, generator=g), torch.randn(2, generator=g), torch.randn(1, 64, generator=g), torch.randn(1, generator=g)
+    outh = torch.empty(1, 3, 3, 15, device=dev())
+    ad, wad, bad, od, wod, bod = [v.to(dev()) for v in (a, wa, ba, o, wo, bo)]
+    check(lib().lfdm_unet_heads(ptr(ad), ptr(wad), ptr(bad), 2, ptr(od), ptr(wod), ptr(bod), 1, 64, 1, 3, 15, ptr(outh),
+                                stream()), "heads64")
+    ref = torch.cat([F.linear(a, wa, ba), F.linear(o, wo, bo)], 1).reshape(1, 3, 15, 3).permute(0, 3, 1, 2)
+    close(outh, ref, "heads64", rtol=1e-4, atol=1e-5)
