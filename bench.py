@@ -22,6 +22,11 @@ sys.path.insert(0, ROOT)
 
 FRAMES = 40
 UNET_GFLOP_REF = 235.10       # reference-executed FLOPs per UNet eval per sample
+# dram__bytes_read.sum + dram__bytes_write.sum of the 94 conv_tc_kernel launches of one UNet evaluation at the bench
+# geometry, per launch, from the ncu pass committed as profiles/r01_launches_eval_summary.md (tools/measure_round.sh):
+# 5.07 GB read + 4.39 GB written per evaluation.  Not measured live (ncu cannot wrap the timed region).
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 100.58e6
+NCU_CONV_TRAFFIC_SOURCE = "profiles/r01_launches_eval_summary.md (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, one UNet evaluation)"
 UNET_GFLOP_ALGO = 169.3       # after the legal hoists (what the kernels must do)
 WARP_MB_PER_FRAME = 25.1      # K12 algorithmic bytes per frame per sample
 
@@ -271,13 +276,17 @@ def main():
         ev1.record()
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
-        tc = [(f, a.elapsed_time(b)) for (_, e, f, a, b) in prof if e == "tc"]
-        simt = [(f, a.elapsed_time(b)) for (_, e, f, a, b) in prof if e != "tc"]
+        tc = [(f, a.elapsed_time(b)) for (_, e, f, a, b, _) in prof if e == "tc"]
+        simt = [(f, a.elapsed_time(b)) for (_, e, f, a, b, _) in prof if e != "tc"]
         tc_ms, tc_fl = sum(t for _, t in tc), sum(f for f, _ in tc)
+        tc_bytes = sum(ab for (_, e, _, _, _, ab) in prof if e == "tc")
         achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, split-bf16 x3)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": None, "peak_source": pk["src"] + " bf16 sustained", "launches": len(tc),
+                "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch (dram read+write, ncu)",
+                "traffic_source": NCU_CONV_TRAFFIC_SOURCE,
+                "algorithmic_bytes_per_launch": tc_bytes / max(1, len(tc)),
+                "peak_source": pk["src"] + " bf16 sustained", "launches": len(tc),
                 "avg_launch_ms": tc_ms / max(1, len(tc)), "algorithmic_gflop_per_eval": tc_fl / 1e9,
                 "executed_mma_flops_x": 3, "conv_ms_per_eval": tc_ms, "simt_conv_ms_per_eval": sum(t for _, t in simt),
                 "unet_eval_ms_eager": ev0.elapsed_time(ev1)}

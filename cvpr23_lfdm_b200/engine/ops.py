@@ -157,7 +157,12 @@ class ConvLayer:
             ev1.record()
             eff_taps = self.kh * self.kw if self.mode == L.CONV_DIRECT else 4   # post-hoist: 2x2 sub-kernels per output
             flops = 2.0 * nf * ho * wo * self.cout * self.cin * eff_taps
-            PROFILE.append((self.name, self.last_engine, flops, ev0, ev1))
+            # algorithmic bytes: every operand once (activations 4 B/element in either format, packed weights 4 B/element)
+            m_in, m_out = nf * h * w, nf * ho * wo
+            abytes = 4.0 * (m_in * self.cin + self.cout * self.cin * self.kh * self.kw
+                            + m_out * self.cout * ((out_f32 is not None) + (out_sb is not None))
+                            + (0 if residual is None else residual.numel()))
+            PROFILE.append((self.name, self.last_engine, flops, ev0, ev1, abytes))
         if gn_stats is not None and not fused_stats:
             assert out_f32 is not None
             check(lib().lfdm_gn_stats(ptr(out_f32), out_f32.shape[0], self.cout, gn_groups, rows_per_sample,

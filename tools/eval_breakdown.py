@@ -35,7 +35,7 @@ e1.record()
 torch.cuda.synchronize()
 prof, ops.PROFILE = ops.PROFILE, None
 agg = collections.OrderedDict()
-for name, engine, flops, a, b in prof:
+for name, engine, flops, a, b, _ in prof:
     k = (name, engine, round(flops / 1e9, 2))
     t = a.elapsed_time(b)
     n, s = agg.get(k, (0, 0.0))
