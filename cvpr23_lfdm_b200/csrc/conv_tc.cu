@@ -1,16 +1,26 @@
 // conv_tc.cu — LFDM_ENGINE_TC: persistent, warp-specialised tcgen05 implicit-GEMM convolution for sm_100a.
 //
-//   D[128 x BN] (fp32, TMEM, double-buffered) += A[128 x 64] * B[BN x 64]^T     per (filter tap, 64-channel chunk)
+//   D[128 x BN] (fp32, TMEM accumulator ring) += A[128 x 64] * B[BN x 64]^T     per (filter tap, 64-channel chunk)
 //
 // * A tiles are gathered straight from the channels-last split-bf16 activation tensor by TMA: one 5-D box
 //   {64 ch, BW, BH, BNF, plane} per tap, shifted by the tap offset; out-of-bounds coordinates are zero-filled by
 //   the TMA unit, which *is* the zero padding of the convolution.  A "virtual concat" (torch.cat of the UNet skip
-//   connections) is two tensor maps walked back to back.  Stride-2 convs read four parity views of the input.
-// * B tiles (weights, pre-split to bf16 hi/lo and packed [tap][Cout][Cin]) come from a 4-D map.
-// * fp32-class accuracy on bf16 tensor cores: x*w ~ hi*hi + hi*lo + lo*hi (3 tcgen05.mma per K step, fp32 accum).
-// * warp roles: warp0 = TMA producer, warp1 = MMA issuer (one elected thread), warp2 = TMEM allocator,
-//   warps4-7 = epilogue (tcgen05.ld -> bias/residual/activation/GroupNorm partial sums -> global stores).
-//   smem ring: full/empty mbarriers; TMEM ring: 2 accumulator stages, tmem_full/tmem_empty mbarriers.
+//   connections) is two tensor maps walked back to back.  Stride-2 convs read four parity views of the input;
+//   transposed / up-sampling convs run as four 2x2 phase launches.
+// * 3x3 "halo mode" (tile inside one image, BW <= 32): one (BH+2)-row halo copy per horizontal tap offset; the three
+//   vertical taps are descriptor start offsets into it.  Separate A (2 x 48 KiB) and B (single-tap) rings, one
+//   producer warp each.
+// * B tiles (weights, pre-split to bf16 hi/lo and packed [plane][tap][Cout][Cin]) come from a 4-D map; W_hi / W_lo
+//   of a tap sit back to back so one N = 2*BN MMA covers both.
+// * fp32-class accuracy on bf16 tensor cores: x*w ~ hi*hi + hi*lo + lo*hi, fp32 accumulate (2 MMAs per K-step in
+//   the wide form, 3 in the classic form used for the short-K projections).
+// * warp roles: warp0 = TMA producer (A in halo mode), warp1 = MMA issuer (one elected thread runs the whole loop),
+//   warp2 = TMEM allocator, warp3 = B producer (halo mode), warps 4-11 = two epilogue groups draining alternate
+//   tiles (tcgen05.ld -> bias / residual / activation / GroupNorm partial sums -> swizzled smem stage -> TMA store,
+//   or coalesced global stores when a residual / split-bf16 output is involved).
+//   smem ring: full/empty mbarriers; TMEM ring: 2-4 accumulator stages, tmem_full/tmem_empty mbarriers.
+// * launched with the programmatic-dependent-launch attribute: everything above pdl_wait() overlaps the previous
+//   kernel's tail.
 //
 // Replaces cuDNN/cuBLAS behind every Conv3d(1,k,k)/ConvTranspose3d/Conv2d/Linear on the path (include/lfdm_b200.h).
 #include <cuda.h>
@@ -25,7 +35,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;               // bf16 elements per K block = 128 bytes = one swizzle row
 constexpr int A_BYTES = BM * BK * 2; // 16 KiB per plane
 constexpr int MAX_TAPS = 52;
-constexpr int NUM_THREADS = 384;     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+constexpr int NUM_THREADS = 384;     // warp0 TMA (A), warp1 MMA, warp2 TMEM alloc, warp3 TMA (B, halo mode), warps 4-11 epilogue
 
 struct TcArgs {
     CUtensorMap tmA[8];              // [source*4 + parity view]
