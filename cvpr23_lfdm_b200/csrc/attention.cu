@@ -644,6 +644,288 @@ __global__ void __launch_bounds__(128, 3) attn_softmax_mma16_kernel(const float*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v2 of the same kernel: 16 resident warps per SM instead of 12 and ~40 % fewer instructions per unit.
+//  * K and V land as fp32 (cp.async) and are converted ONCE, in place, to split-bf16 planes (hi | lo, 40 rows x 64 B,
+//    16-byte chunks XOR-swizzled by (row >> 1) & 3); rotary is applied to K during that pass.  Every B fragment is
+//    then an ldmatrix (.trans for V) of ready-made bf16 pairs: no per-fragment splits, no bank conflicts, no padding.
+//  * Q never touches shared memory: the A fragments are float2 loads straight from global (each element belongs to
+//    exactly one lane; 8 rows x 32 B per instruction = full sectors), scaled, rotated and split in registers, and the
+//    next 16-row tile's Q is prefetched while the current one is processed.
+//  * the three 16-row query tiles run one after the other (S: 20, O: 16 accumulators) -> <= 128 registers, 50 KiB of
+//    smem per CTA -> 4 CTAs per SM.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KV_PLANE = ML * 64;                        // one bf16 plane: 40 rows x 32 dims
+constexpr int OST_PITCH = 40;                            // O staging pitch (floats): conflict-free float2 stores
+constexpr int V2_WARP_BYTES = 4 * KV_PLANE + 16 * OST_PITCH * 4;
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// byte offset of 16-byte chunk `chunk` (8 dims) of row `row` inside a swizzled plane
+__device__ __forceinline__ int kv_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
+
+__global__ void __launch_bounds__(128, 4) attn_softmax_mma16v2_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
+                                                                      int64_t out_plane, float* __restrict__ out_f32,
+                                                                      int64_t n_seq, int L, int heads, int64_t inner,
+                                                                      int64_t outer_stride, int64_t inner_stride,
+                                                                      int64_t row_stride, const float* __restrict__ rot_cos,
+                                                                      const float* __restrict__ rot_sin,
+                                                                      const float* __restrict__ pos_bias) {
+    pdl_prologue_done();
+    extern __shared__ __align__(16) uint8_t s_dyn2[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t unit = (int64_t)blockIdx.x * 4 + w;
+    if (unit >= n_seq * heads) return;
+    uint8_t* wb = s_dyn2 + (size_t)w * V2_WARP_BYTES;
+    float* kraw = reinterpret_cast<float*>(wb);                       // [40][32] fp32  -> K_hi | K_lo planes
+    float* vraw = reinterpret_cast<float*>(wb + 2 * KV_PLANE);        // [40][32] fp32  -> V_hi | V_lo planes
+    float* ost = reinterpret_cast<float*>(wb + 4 * KV_PLANE);         // [16][OST_PITCH] fp32 output staging
+    const int64_t s = unit / heads;
+    const int h = (int)(unit - s * heads);
+    const int hid = heads * DH;
+    const int64_t base = (s / inner) * outer_stride + (s % inner) * inner_stride;
+    const int64_t rstep = row_stride * (3 * hid);
+    const float* src0 = qkv + base * (3 * hid) + h * DH;
+    const float scale = 0.17677669529663687f;  // 32^-0.5
+    const int g = lane >> 2, t = lane & 3;
+
+    // ---- K, V: asynchronous fp32 landing
+    for (int idx = lane; idx < L * 8; idx += 32) {
+        const int j = idx >> 3, seg = idx & 7;
+        const float* sr = src0 + (int64_t)j * rstep + seg * 4;
+        cp_async16(kraw + j * 32 + seg * 4, sr + hid);
+        cp_async16(vraw + j * 32 + seg * 4, sr + 2 * hid);
+    }
+    cp_async_commit();
+    for (int idx = lane; idx < (ML - L) * 8; idx += 32) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(kraw + L * 32 + idx * 4) = z;
+        *reinterpret_cast<float4*>(vraw + L * 32 + idx * 4) = z;
+    }
+    // ---- Q fragments of query tile 0 straight from global: rows (g, g+8), columns 16 ks + 2t (+8)
+    float2 qn[2][4];
+    auto load_q = [&](int mt) {
+        const int r0 = 16 * mt + g, r1 = r0 + 8;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int c = 16 * ks + 2 * t;
+            const float2 z = make_float2(0.f, 0.f);
+            qn[ks][0] = r0 < L ? *reinterpret_cast<const float2*>(src0 + (int64_t)r0 * rstep + c) : z;
+            qn[ks][1] = r1 < L ? *reinterpret_cast<const float2*>(src0 + (int64_t)r1 * rstep + c) : z;
+            qn[ks][2] = r0 < L ? *reinterpret_cast<const float2*>(src0 + (int64_t)r0 * rstep + c + 8) : z;
+            qn[ks][3] = r1 < L ? *reinterpret_cast<const float2*>(src0 + (int64_t)r1 * rstep + c + 8) : z;
+        }
+    };
+    load_q(0);
+    cp_async_wait<0>();
+    __syncwarp();
+
+    // ---- one pass: K (rotary) and V -> split-bf16 planes, in place (all reads of a tile precede its first write)
+    {
+        float4 kr[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) kr[i] = *reinterpret_cast<const float4*>(kraw + (lane + 32 * i) * 4);
+        __syncwarp();
+        uint8_t* khi = reinterpret_cast<uint8_t*>(kraw);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const int idx = lane + 32 * i, j = idx >> 3, c4 = idx & 7;
+            float4 v = kr[i];
+            if (rot_cos && j < L) {
+                const float c0 = rot_cos[j * (DH / 2) + 2 * c4], s0 = rot_sin[j * (DH / 2) + 2 * c4];
+                const float c1 = rot_cos[j * (DH / 2) + 2 * c4 + 1], s1 = rot_sin[j * (DH / 2) + 2 * c4 + 1];
+                v = make_float4(v.x * c0 - v.y * s0, v.y * c0 + v.x * s0, v.z * c1 - v.w * s1, v.w * c1 + v.z * s1);
+            }
+            uint2 hv, lv;
+            split_bf16x2(v.x, v.y, hv.x, lv.x);
+            split_bf16x2(v.z, v.w, hv.y, lv.y);
+            const int off = kv_off(j, c4 >> 1) + ((c4 & 1) << 3);
+            *reinterpret_cast<uint2*>(khi + off) = hv;
+            *reinterpret_cast<uint2*>(khi + KV_PLANE + off) = lv;
+        }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) kr[i] = *reinterpret_cast<const float4*>(vraw + (lane + 32 * i) * 4);
+        __syncwarp();
+        uint8_t* vhi = reinterpret_cast<uint8_t*>(vraw);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const int idx = lane + 32 * i, j = idx >> 3, c4 = idx & 7;
+            uint2 hv, lv;
+            split_bf16x2(kr[i].x, kr[i].y, hv.x, lv.x);
+            split_bf16x2(kr[i].z, kr[i].w, hv.y, lv.y);
+            const int off = kv_off(j, c4 >> 1) + ((c4 & 1) << 3);
+            *reinterpret_cast<uint2*>(vhi + off) = hv;
+            *reinterpret_cast<uint2*>(vhi + KV_PLANE + off) = lv;
+        }
+    }
+    __syncwarp();
+
+    const uint32_t k_sa = smem_addr_u32(kraw), v_sa = smem_addr_u32(vraw);
+    const int lt = lane >> 3, lr = lane & 7;                 // ldmatrix: this lane supplies row lr of tile lt
+    const float* pb = pos_bias ? pos_bias + (int64_t)h * L * L : nullptr;
+    const bool pair_ok = (L & 1) == 0 && (reinterpret_cast<uintptr_t>(pos_bias) & 7) == 0;
+
+#pragma unroll 1
+    for (int mt = 0; mt < 3; ++mt) {
+        if (16 * mt >= L) break;
+        const int i0 = 16 * mt + g, i1 = i0 + 8;
+        // ---- A fragments of this query tile: scale, rotary (reference :325-331), split
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 q2 = qn[ks][e];
+                q2.x *= scale; q2.y *= scale;
+                if (rot_cos) {
+                    const int row = (e & 1) ? i1 : i0;
+                    if (row < L) {
+                        const int pr = 8 * ks + t + ((e >> 1) << 2);
+                        const float c = rot_cos[row * (DH / 2) + pr], sn = rot_sin[row * (DH / 2) + pr];
+                        q2 = make_float2(q2.x * c - q2.y * sn, q2.y * c + q2.x * sn);
+                    }
+                }
+                split_bf16x2(q2.x, q2.y, ah[ks][e], al[ks][e]);
+            }
+        if (16 * (mt + 1) < L) load_q(mt + 1);               // prefetch the next tile's Q behind this tile's math
+
+        // ---- S = Q K^T : B fragments by ldmatrix from the K planes (tiles: 8 keys x 8 dims)
+        float acc[5][4];
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {                 // key tiles (2np, 2np+1): regs {b0, b1} of each
+                const int key = 8 * (2 * np + (lt >> 1)) + lr, chunk = 2 * ks + (lt & 1);
+                uint32_t kh4[4], kl4[4];
+                ldmatrix_x4(kh4, k_sa + kv_off(key, chunk));
+                ldmatrix_x4(kl4, k_sa + KV_PLANE + kv_off(key, chunk));
+                const uint32_t bh0[2] = {kh4[0], kh4[1]}, bl0[2] = {kl4[0], kl4[1]};
+                const uint32_t bh1[2] = {kh4[2], kh4[3]}, bl1[2] = {kl4[2], kl4[3]};
+                mma3_bf16(acc[2 * np], ah[ks], al[ks], bh0, bl0);
+                mma3_bf16(acc[2 * np + 1], ah[ks], al[ks], bh1, bl1);
+            }
+            {
+                const int key = 32 + lr, chunk = 2 * ks + (lt & 1);      // key tile 4: lanes 0-15 supply the addresses
+                uint32_t kh2[2], kl2[2];
+                ldmatrix_x2(kh2, k_sa + kv_off(key, chunk));
+                ldmatrix_x2(kl2, k_sa + KV_PLANE + kv_off(key, chunk));
+                mma3_bf16(acc[4], ah[ks], al[ks], kh2, kl2);
+            }
+        }
+        // ---- bias + row softmax in registers (a row lives in the 4 lanes that share g)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int i = half ? i1 : i0;
+            const bool row_ok = i < L;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) {
+                const int j0 = 8 * nt + 2 * t;
+                float2 b2 = make_float2(0.f, 0.f);
+                if (pb && row_ok) {
+                    if (pair_ok) { if (j0 < L) b2 = *reinterpret_cast<const float2*>(pb + i * L + j0); }
+                    else { if (j0 < L) b2.x = pb[i * L + j0]; if (j0 + 1 < L) b2.y = pb[i * L + j0 + 1]; }
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float v = acc[nt][2 * half + e] + (e ? b2.y : b2.x);
+                    v = (j0 + e < L) ? v : -INFINITY;
+                    acc[nt][2 * half + e] = v;
+                    mx = fmaxf(mx, v);
+                }
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float ex = __expf(acc[nt][2 * half + e] - mx);
+                    acc[nt][2 * half + e] = ex;
+                    sum += ex;
+                }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) { acc[nt][2 * half] *= inv; acc[nt][2 * half + 1] *= inv; }
+        }
+        // ---- O = P V : A fragments from the C fragments of S; B fragments by ldmatrix.trans from the V planes
+        float o[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            uint32_t ph[4], pl[4];
+            split_bf16x2(acc[2 * ks][0], acc[2 * ks][1], ph[0], pl[0]);
+            split_bf16x2(acc[2 * ks][2], acc[2 * ks][3], ph[1], pl[1]);
+            if (2 * ks + 1 < 5) {
+                split_bf16x2(acc[2 * ks + 1][0], acc[2 * ks + 1][1], ph[2], pl[2]);
+                split_bf16x2(acc[2 * ks + 1][2], acc[2 * ks + 1][3], ph[3], pl[3]);
+            } else {
+                ph[2] = pl[2] = ph[3] = pl[3] = 0u;
+            }
+            if (ks < 2) {
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {             // dim tiles (2np, 2np+1): tiles {keys 16ks.., keys 16ks+8..} of each
+                    const int key = 16 * ks + 8 * (lt & 1) + lr, chunk = 2 * np + (lt >> 1);
+                    uint32_t vh4[4], vl4[4];
+                    ldmatrix_x4_trans(vh4, v_sa + kv_off(key, chunk));
+                    ldmatrix_x4_trans(vl4, v_sa + KV_PLANE + kv_off(key, chunk));
+                    const uint32_t bh0[2] = {vh4[0], vh4[1]}, bl0[2] = {vl4[0], vl4[1]};
+                    const uint32_t bh1[2] = {vh4[2], vh4[3]}, bl1[2] = {vl4[2], vl4[3]};
+                    mma3_bf16(o[2 * np], ph, pl, bh0, bl0);
+                    mma3_bf16(o[2 * np + 1], ph, pl, bh1, bl1);
+                }
+            } else {                                         // keys 32..39 only (40..47 do not exist: zero B halves)
+                const int key = 32 + lr, chunk = lt;         // four dim tiles of the same 8 keys
+                uint32_t vh4[4], vl4[4];
+                ldmatrix_x4_trans(vh4, v_sa + kv_off(key, chunk));
+                ldmatrix_x4_trans(vl4, v_sa + KV_PLANE + kv_off(key, chunk));
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const uint32_t bh[2] = {vh4[nt], 0u}, bl[2] = {vl4[nt], 0u};
+                    mma3_bf16(o[nt], ph, pl, bh, bl);
+                }
+            }
+        }
+        // ---- stage the 16 x 32 output tile, then coalesced row stores
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            *reinterpret_cast<float2*>(ost + g * OST_PITCH + 8 * nt + 2 * t) = make_float2(o[nt][0], o[nt][1]);
+            *reinterpret_cast<float2*>(ost + (g + 8) * OST_PITCH + 8 * nt + 2 * t) = make_float2(o[nt][2], o[nt][3]);
+        }
+        __syncwarp();
+        for (int idx = lane; idx < 16 * 8; idx += 32) {
+            const int r = idx >> 3, seg = idx & 7, i = 16 * mt + r;
+            if (i < L) {
+                const float4 v = *reinterpret_cast<const float4*>(ost + r * OST_PITCH + seg * 4);
+                const int64_t oi = (base + (int64_t)i * row_stride) * hid + h * DH + seg * 4;
+                if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi) = v;
+                if (out_sb) store_sb4(out_sb, out_plane, oi, v);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // one block (4 warps) per (frame, head).  Every warp streams 32-row chunks of (k, v) and later q through a
 // double-buffered cp.async pipeline (all bytes of the next chunk are in flight while the current one is consumed);
 // exp / softmax of a row is computed once and kept in the smem tile; the 32x32 context and its application to q are
@@ -1007,6 +1289,21 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
     if (seq_len <= 40) {
         static const bool use_mma = (getenv("LFDM_ATTN_SIMT") == nullptr);      // A/B switch: CUDA-core tiling instead
         static const bool use_tf32 = (getenv("LFDM_ATTN_TF32") != nullptr);      // A/B switch: 3xTF32 m16n8k8 form
+        static const bool use_v1 = (getenv("LFDM_ATTN_V1") != nullptr);          // A/B switch: first mma.m16n8k16 kernel
+        if (use_mma && !use_tf32 && !use_v1 && seq_len >= 17) {
+            const size_t smem = (size_t)4 * V2_WARP_BYTES;
+            static bool attr2 = false;
+            if (!attr2) {
+                cudaError_t e = cudaFuncSetAttribute(attn_softmax_mma16v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return (int)e;
+                attr2 = true;
+            }
+            const int64_t units = n_seq * heads;
+            LFDM_LAUNCH_PDL(attn_softmax_mma16v2_kernel, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
+                            qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
+                            row_stride, rot_cos, rot_sin, pos_bias);
+            return 0;
+        }
         if (use_mma && !use_tf32) {
             const size_t smem = sizeof(float) * 4 * (2 * ML * QP2 + ML * VP2);
             static bool attr16 = false;

@@ -252,7 +252,33 @@ def test_attn_temporal_and_spatial():
     close(out, ref_s, "spatial attention")
 
 
-@pytest.mark.parametrize("L", [5, 24, 40, 49, 64])
+@pytest.mark.parametrize("f", [17, 24, 33, 39])
+def test_attn_temporal_ragged_lengths(f):
+    """rotary + bias on frame counts that leave partial 16-row query tiles / odd bias rows (ldmatrix kernel, 17 <= L <= 40)"""
+    from oracle import lfdm_oracle as O
+    from cvpr23_lfdm_b200.engine import ops
+    g = torch.Generator().manual_seed(60 + f)
+    b, p, heads = 2, 6, 3
+    hid = heads * 32
+    qkv = torch.randn(b, f, p, 3 * hid, generator=g)
+    bias = torch.randn(heads, f, f, generator=g)
+    freqs = O.rotary_freqs(32)
+    x = qkv.permute(0, 2, 1, 3)
+    q, k, v = [t.reshape(b, p, f, heads, 32).transpose(-2, -3) for t in x.chunk(3, -1)]
+    q = O.rotary_apply(q * 32 ** -0.5, freqs)
+    k = O.rotary_apply(k, freqs)
+    sim = torch.einsum("...hid,...hjd->...hij", q, k) + bias
+    att = (sim - sim.amax(-1, keepdim=True)).softmax(-1)
+    o = torch.einsum("...hij,...hjd->...hid", att, v).transpose(-2, -3).reshape(b, p, f, hid)
+    ref = o.permute(0, 2, 1, 3).reshape(b * f * p, hid)
+    ang = torch.outer(torch.arange(f).float(), freqs)
+    out = torch.empty(b * f * p, hid, device=dev())
+    ops.attn_softmax(qkv.reshape(b * f * p, 3 * hid).to(dev()), None, out, b * p, f, heads, p, f * p, 1, p,
+                     ang.cos().contiguous().to(dev()), ang.sin().contiguous().to(dev()), bias.to(dev()))
+    close(out, ref, f"temporal attention f={f}")
+
+
+@pytest.mark.parametrize("L", [5, 17, 24, 31, 33, 40, 49, 64])
 def test_attn_softmax_lengths(L):
     """every register-tile configuration of the softmax attention core (L <= 16, <= 40, <= 64 with two row passes)"""
     from cvpr23_lfdm_b200.engine import ops

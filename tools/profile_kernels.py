@@ -82,6 +82,18 @@ def cases():
         return run, 4.0 * B * p * heads * F * F * 32, m * 768 * 4 + m * 256 * 4, lambda: "mma.sync split-bf16"
     c["attn_temporal_32"] = attn_t
 
+    def attn_tc():
+        # same problem, sequences contiguous in memory ((b, pixel) major, frame minor): what the gather pattern costs
+        p, heads = 1024, 8
+        m = B * F * p
+        qkv = torch.randn(m, 768, device=dev)
+        o = SB(m, 256, dev)
+        ang = torch.outer(torch.arange(F, device=dev).float(), 1.0 / (10000 ** (torch.arange(0, 32, 2, device=dev).float() / 32)))
+        cs, sn, bias = ang.cos().contiguous(), ang.sin().contiguous(), torch.randn(heads, F, F, device=dev)
+        run = lambda: ops.attn_softmax(qkv, o, None, B * p, F, heads, 1, F, 0, 1, cs, sn, bias)
+        return run, 4.0 * B * p * heads * F * F * 32, m * 768 * 4 + m * 256 * 4, lambda: "mma.sync split-bf16, contiguous sequences"
+    c["attn_temporal_32_contig"] = attn_tc
+
     def attn_l():
         p, heads = 1024, 8
         m = B * F * p
