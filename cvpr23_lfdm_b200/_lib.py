@@ -29,6 +29,8 @@ class ConvDesc(C.Structure):
         ("residual", C.c_void_p), ("res_bcast_f", C.c_int32), ("out_f32", C.c_void_p), ("f32_act", C.c_int32),
         ("out_sb", C.c_void_p), ("out_plane", C.c_int64), ("sb_act", C.c_int32), ("sb_scale", C.c_void_p),
         ("sb_shift", C.c_void_p), ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("rows_per_sample", C.c_int32),
+        ("rot_cos", C.c_void_p), ("rot_sin", C.c_void_p), ("rot_frames", C.c_int32), ("rot_rows_per_frame", C.c_int32),
+        ("rot_cols", C.c_int32), ("rot_scale_cols", C.c_int32), ("rot_scale", C.c_float),
     ]
 
 
@@ -55,6 +57,7 @@ def _declare(l):
         "lfdm_gn_apply": [vp, vp, vp, vp, vp, i64, vp, vp, vp, i64, i64, i32, i32, i32, f32, vp],
         "lfdm_layernorm": [vp, vp, vp, i64, vp, i64, i32, f32, vp],
         "lfdm_attn_softmax": [vp, vp, i64, vp, i64, i32, i32, i64, i64, i64, i64, vp, vp, vp, vp],
+        "lfdm_attn_softmax_pre": [vp, vp, i64, vp, i64, i32, i32, i64, i64, i64, i64, vp, vp],
         "lfdm_attn_linear": [vp, vp, i64, vp, i64, i32, i32, vp],
         "lfdm_small_linear": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "lfdm_sinusoidal": [vp, vp, vp, i32, i32, vp],
@@ -83,7 +86,8 @@ def _declare(l):
         fn.restype = C.c_int
 
 
-EXPORTED = ["lfdm_conv", "lfdm_gn_stats", "lfdm_gn_apply", "lfdm_layernorm", "lfdm_attn_softmax", "lfdm_attn_linear",
+EXPORTED = ["lfdm_conv", "lfdm_gn_stats", "lfdm_gn_apply", "lfdm_layernorm", "lfdm_attn_softmax", "lfdm_attn_softmax_pre",
+            "lfdm_attn_linear",
             "lfdm_small_linear", "lfdm_sinusoidal", "lfdm_ss_combine", "lfdm_sampler_x0", "lfdm_sampler_quantile",
             "lfdm_sampler_update", "lfdm_warp_blend_rows", "lfdm_warp_blend_image", "lfdm_to_rows", "lfdm_from_rows",
             "lfdm_im2col_small", "lfdm_avgpool2_rows", "lfdm_unet_heads", "lfdm_split_bf16", "lfdm_version",

@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(128, 4) attn_softmax_mma16v2_kernel(const floa
                                                                       int64_t outer_stride, int64_t inner_stride,
                                                                       int64_t row_stride, const float* __restrict__ rot_cos,
                                                                       const float* __restrict__ rot_sin,
-                                                                      const float* __restrict__ pos_bias) {
+                                                                      const float* __restrict__ pos_bias, int q_prescaled) {
     pdl_prologue_done();
     extern __shared__ __align__(16) uint8_t s_dyn2[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(128, 4) attn_softmax_mma16v2_kernel(const floa
     const int64_t base = (s / inner) * outer_stride + (s % inner) * inner_stride;
     const int64_t rstep = row_stride * (3 * hid);
     const float* src0 = qkv + base * (3 * hid) + h * DH;
-    const float scale = 0.17677669529663687f;  // 32^-0.5
+    const float scale = q_prescaled ? 1.f : 0.17677669529663687f;  // 32^-0.5 (already applied by the qkv epilogue when fused)
     const int g = lane >> 2, t = lane & 3;
 
     // ---- K, V: asynchronous fp32 landing
@@ -1301,7 +1301,7 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
             const int64_t units = n_seq * heads;
             LFDM_LAUNCH_PDL(attn_softmax_mma16v2_kernel, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
                             qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
-                            row_stride, rot_cos, rot_sin, pos_bias);
+                            row_stride, rot_cos, rot_sin, pos_bias, 0);
             return 0;
         }
         if (use_mma && !use_tf32) {
@@ -1337,6 +1337,22 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
     }
     return launch_attn_softmax<8, 8, false>(LFDM_ATTN_ARGS);        // L <= 64: two row passes of 32
 #undef LFDM_ATTN_ARGS
+}
+
+extern "C" int lfdm_attn_softmax_pre(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_seq,
+                                     int seq_len, int heads, int64_t inner, int64_t outer_stride, int64_t inner_stride,
+                                     int64_t row_stride, const float* pos_bias, void* stream) {
+    if (!qkv || heads <= 0 || inner <= 0) return LFDM_E_BADARG;
+    if (seq_len < 17 || seq_len > ML) return LFDM_E_UNSUPP;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)4 * V2_WARP_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(attn_softmax_mma16v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t units = n_seq * heads;
+    LFDM_LAUNCH_PDL(attn_softmax_mma16v2_kernel, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
+                    qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
+                    row_stride, (const float*)nullptr, (const float*)nullptr, pos_bias, 1);
+    return 0;
 }
 
 extern "C" int lfdm_attn_linear(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_frames,

@@ -7,7 +7,7 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t stream);
 extern "C" int lfdm_conv(const lfdm_conv_desc* d, int engine, void* stream) {
     if (!d) return LFDM_E_BADARG;
     if (engine == LFDM_ENGINE_TC) return lfdm_conv_tc(d, (cudaStream_t)stream);
-    if (engine == LFDM_ENGINE_SIMT) return lfdm_conv_simt(d, (cudaStream_t)stream);
+    if (engine == LFDM_ENGINE_SIMT) return d->rot_cos ? LFDM_E_UNSUPP : lfdm_conv_simt(d, (cudaStream_t)stream);
     return LFDM_E_BADARG;
 }
 

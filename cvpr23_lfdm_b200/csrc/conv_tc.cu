@@ -65,6 +65,10 @@ struct TcArgs {
     double* gn_stats;
     int32_t gn_cpg, gn_groups;
     int64_t rows_per_sample;
+    const float* rot_cos;            // fused rotary of a temporal qkv projection (TMA-store epilogue only), see lfdm_conv_desc
+    const float* rot_sin;
+    int32_t rot_frames, rot_rows_per_frame, rot_cols, rot_scale_cols;
+    float rot_scale;
 };
 
 // epilogue of 16 accumulator columns [nb, nb+16) of one output row
@@ -568,6 +572,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                             }
                         }
+                        if (a.rot_cos && nb < a.rot_cols) {
+                            // q (scaled) / k block of one head: rotate the 16 (2i, 2i+1) pairs by this row's frame angle
+                            const int fr = (int)((orow / a.rot_rows_per_frame) % a.rot_frames);
+                            const float sc = nb < a.rot_scale_cols ? a.rot_scale : 1.f;
+                            const float4* c4p = reinterpret_cast<const float4*>(a.rot_cos + fr * 16);
+                            const float4* s4p = reinterpret_cast<const float4*>(a.rot_sin + fr * 16);
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd) {
+                                const float4 c4 = c4p[qd], s4 = s4p[qd];
+                                const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float x = v[8 * qd + 2 * e] * sc, y = v[8 * qd + 2 * e + 1] * sc;
+                                    v[8 * qd + 2 * e] = x * cc[e] - y * ss[e];
+                                    v[8 * qd + 2 * e + 1] = y * cc[e] + x * ss[e];
+                                }
+                            }
+                        }
                         if (a.gn_stats) {
 #pragma unroll
                             for (int oct = 0; oct < 4; ++oct) {        // cpg is a multiple of 8: one (sum, sumsq) per 8 columns
@@ -800,6 +822,13 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
     {
         static const int dbg = getenv("LFDM_CONV_DBG") ? atoi(getenv("LFDM_CONV_DBG")) : 0;
         a.dbg = dbg;
+    }
+    if (d->rot_cos) {
+        if (!a.tma_store || !d->rot_sin || d->rot_frames <= 0 || d->rot_rows_per_frame <= 0 || (d->rot_cols % 32) || (d->rot_scale_cols % 32) ||
+            d->rot_cols > d->c_out || ((reinterpret_cast<uintptr_t>(d->rot_cos) | reinterpret_cast<uintptr_t>(d->rot_sin)) & 15))
+            return LFDM_E_UNSUPP;
+        a.rot_cos = d->rot_cos; a.rot_sin = d->rot_sin; a.rot_frames = d->rot_frames; a.rot_rows_per_frame = d->rot_rows_per_frame;
+        a.rot_cols = d->rot_cols; a.rot_scale_cols = d->rot_scale_cols; a.rot_scale = d->rot_scale;
     }
     a.chunks[0] = d->a_c[0] / BK;
     a.chunks[1] = nsrc > 1 ? d->a_c[1] / BK : 0;

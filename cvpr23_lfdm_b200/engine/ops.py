@@ -99,8 +99,11 @@ class ConvLayer:
         return 2 * h + 2 * self.pad - self.kh + 1, 2 * w + 2 * self.pad - self.kw + 1
 
     def __call__(self, srcs, nf, h, w, *, out_f32=None, out_sb=None, residual=None, res_bcast_f=0, f32_act=0,
-                 sb_act=0, sb_scale=None, sb_shift=None, gn_stats=None, gn_groups=8, rows_per_sample=0, stats_zeroed=False):
-        """srcs: list of SB or F32 row matrices (one per virtual-concat source)."""
+                 sb_act=0, sb_scale=None, sb_shift=None, gn_stats=None, gn_groups=8, rows_per_sample=0, stats_zeroed=False,
+                 rot=None):
+        """srcs: list of SB or F32 row matrices (one per virtual-concat source).
+        rot = (cos, sin, frames, rows_per_frame, rot_cols, scale_cols, scale): fuse q-scale + q/k rotary into the epilogue
+        (tcgen05 engine, plain F32 output); `self.rot_applied` tells the caller whether the engine took it."""
         ho, wo = self.out_hw(h, w)
         a_sb = [None, None]
         a_f32 = [None, None]
@@ -125,6 +128,10 @@ class ConvLayer:
                   out_f32=out_f32, f32_act=f32_act, out_sb=out_sb.t if out_sb is not None else None,
                   out_plane=out_sb.plane if out_sb is not None else 0, sb_act=sb_act, sb_scale=sb_scale,
                   sb_shift=sb_shift, gn_stats=None, gn_cpg=0, rows_per_sample=rows_per_sample)
+        self.rot_applied = False
+        if rot is not None:
+            kw.update(rot_cos=rot[0], rot_sin=rot[1], rot_frames=int(rot[2]), rot_rows_per_frame=int(rot[3]),
+                      rot_cols=int(rot[4]), rot_scale_cols=int(rot[5]), rot_scale=float(rot[6]))
         rc = L.E_UNSUPP
         self.last_engine = "simt"
         ev0 = None
@@ -142,6 +149,12 @@ class ConvLayer:
                 else:
                     fused_stats = False
             rc = L.conv(kw, L.ENGINE_TC)
+            if rc == L.E_UNSUPP and rot is not None:       # this geometry cannot fuse the rotary: plain projection instead
+                for k in ("rot_cos", "rot_sin"):
+                    kw[k] = None
+                rc = L.conv(kw, L.ENGINE_TC)
+            elif rc == 0 and rot is not None:
+                self.rot_applied = True
             self.last_engine = "tc"
             if rc == L.E_UNSUPP:
                 self.last_engine = "simt"
@@ -151,6 +164,7 @@ class ConvLayer:
             fused_stats = False
         if rc == L.E_UNSUPP:
             kw["gn_stats"] = None
+            kw["rot_cos"] = kw["rot_sin"] = None
             rc = L.conv(kw, L.ENGINE_SIMT)
         check(rc, f"lfdm_conv[{self.name}]")
         if ev0 is not None:
@@ -196,6 +210,13 @@ def attn_softmax(qkv, out_sb, out_f32, n_seq, seq_len, heads, inner, outer_strid
                                   out_sb.plane if out_sb is not None else 0, ptr(out_f32), n_seq, seq_len, heads, inner,
                                   outer_stride, inner_stride, row_stride, ptr(rot_cos), ptr(rot_sin), ptr(pos_bias),
                                   stream()), "lfdm_attn_softmax")
+
+
+def attn_softmax_pre(qkv, out_sb, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride, row_stride, pos_bias=None):
+    """q | k already scaled + rotated by the qkv projection's epilogue (ConvLayer(..., rot=...))"""
+    check(lib().lfdm_attn_softmax_pre(ptr(qkv), ptr(out_sb.t) if out_sb is not None else None,
+                                      out_sb.plane if out_sb is not None else 0, ptr(out_f32), n_seq, seq_len, heads, inner,
+                                      outer_stride, inner_stride, row_stride, ptr(pos_bias), stream()), "lfdm_attn_softmax_pre")
 
 
 def attn_linear(qkv, out_sb, out_f32, n_frames, n_pos, heads):

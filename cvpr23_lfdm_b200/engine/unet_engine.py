@@ -9,11 +9,18 @@ launches through the C-ABI in the reference's data-flow order.  Legal algebraic 
     plus a per-sample cond term (`build_tables` / `ss_from_tables`).
 """
 import math
+import os
 import torch
 from .. import _lib as L
 from .._lib import SB, ptr, stream, check, lib
 from . import ops
 from .ops import ConvLayer, f32
+
+# LFDM_FUSED_ROTARY=1: q*scale + q/k rotary of the temporal attention applied by the epilogue of its qkv projection
+# (lfdm_conv rot_* + lfdm_attn_softmax_pre) instead of inside the attention kernel.  Off by default: measured on B200 it
+# moves ~0.1 ms per 32x32 call from the attention kernel (16 warps/SM) into the 8 epilogue warps of an HBM-bound GEMM
+# and loses overall (conv 6.45 -> 6.83 ms per evaluation).
+FUSE_ROTARY = os.environ.get("LFDM_FUSED_ROTARY") is not None
 
 
 def _rel_pos_bucket(n, num_buckets=32, max_distance=32):
@@ -239,15 +246,18 @@ class UnetEngine:
         ops.gn_apply(h2, stats2, r.g2, r.b2, None, res, out, out_sb, r.groups, rps, r.eps)
         return out, out_sb
 
-    def _attn_common(self, at, x_f32, nf, h, w, core, want_sb):
+    def _attn_common(self, at, x_f32, nf, h, w, core, want_sb, rot=None):
         dev = self.dev
         m, c = x_f32.shape
         n = SB(m, c, dev)
         ops.layernorm(x_f32, at.gamma, out_sb=n, eps=at.eps)
         qkv = f32(m, 3 * at.hid, dev)
-        at.qkv([n], nf, h, w, out_f32=qkv)
+        at.qkv([n], nf, h, w, out_f32=qkv, rot=rot)
         o = SB(m, at.hid, dev)
-        core(qkv, o)
+        if rot is not None:
+            core(qkv, o, at.qkv.rot_applied)
+        else:
+            core(qkv, o)
         out = f32(m, c, dev)
         out_sb = SB(m, c, dev) if want_sb else None
         at.out([o], nf, h, w, out_f32=out, out_sb=out_sb, residual=x_f32)
@@ -256,8 +266,15 @@ class UnetEngine:
     def _temporal(self, at, x_f32, b, f, h, w, want_sb):
         p = h * w
         bias, cos, sin = self._frame_tables(f)
-        core = lambda qkv, o: ops.attn_softmax(qkv, o, None, b * p, f, at.heads, p, f * p, 1, p, cos, sin, bias)
-        return self._attn_common(at, x_f32, b * f, h, w, core, want_sb)
+        def core(qkv, o, pre=False):
+            if pre:        # q*scale and the q / k rotary were applied by the qkv projection's epilogue
+                ops.attn_softmax_pre(qkv, o, None, b * p, f, at.heads, p, f * p, 1, p, bias)
+            else:
+                ops.attn_softmax(qkv, o, None, b * p, f, at.heads, p, f * p, 1, p, cos, sin, bias)
+        rot = None
+        if FUSE_ROTARY and 17 <= f <= 40:
+            rot = (cos, sin, f, p, 2 * at.hid, at.hid, 32 ** -0.5)
+        return self._attn_common(at, x_f32, b * f, h, w, core, want_sb, rot=rot)
 
     def _mid_spatial(self, at, x_f32, b, f, h, w):
         p = h * w

@@ -80,6 +80,14 @@ typedef struct lfdm_conv_desc {
     double*      gn_stats;     /* [B][groups][2] accumulators (pre-zeroed) or NULL (TC engine only)           */
     int32_t      gn_cpg;       /* channels per group                                                          */
     int32_t      rows_per_sample;
+    /* fused q/k rotary embedding of a temporal-attention qkv projection (TC engine, plain F32 output only): columns
+     * [0, rot_cols) are rotated pairwise (2i, 2i+1) by the angle of frame f = (row / rot_rows_per_frame) % rot_frames,
+     * tables [rot_frames][16] (dim_head 32); columns [0, rot_scale_cols) are multiplied by rot_scale first
+     * (q = q * scale; q, k = rotary(q), rotary(k): Attention.forward video_flow_diffusion.py:325-331).  NULL = off. */
+    const float* rot_cos;
+    const float* rot_sin;
+    int32_t      rot_frames, rot_rows_per_frame, rot_cols, rot_scale_cols;
+    float        rot_scale;
 } lfdm_conv_desc;
 
 int lfdm_conv(const lfdm_conv_desc* d, int engine, void* stream);
@@ -104,6 +112,11 @@ int lfdm_layernorm(const float* x, const float* gamma, void* out_sb, int64_t out
 int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_seq, int seq_len,
                       int heads, int64_t inner, int64_t outer_stride, int64_t inner_stride, int64_t row_stride,
                       const float* rot_cos, const float* rot_sin, const float* pos_bias, void* stream);
+/* same core for q|k that already carry scale and rotary (written by lfdm_conv with rot_cos set): no scaling, no rotary
+ * here.  Only the tensor-core kernel of 17 <= seq_len <= 40 implements it; LFDM_E_UNSUPP otherwise.            */
+int lfdm_attn_softmax_pre(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_seq, int seq_len,
+                          int heads, int64_t inner, int64_t outer_stride, int64_t inner_stride, int64_t row_stride,
+                          const float* pos_bias, void* stream);
 /* SpatialLinearAttention core video_flow_diffusion.py:253-263: per (frame, head) over n = hw positions.        */
 int lfdm_attn_linear(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_frames, int n_pos,
                      int heads, void* stream);

@@ -252,6 +252,38 @@ def test_attn_temporal_and_spatial():
     close(out, ref_s, "spatial attention")
 
 
+def test_qkv_projection_with_fused_rotary_and_prescaled_attention():
+    """lfdm_conv(rot_*) + lfdm_attn_softmax_pre == projection, then q*scale, rotary(q), rotary(k), attention (reference order)"""
+    from oracle import lfdm_oracle as O
+    from cvpr23_lfdm_b200.engine import ops
+    from cvpr23_lfdm_b200.engine.ops import ConvLayer, f32
+    g = torch.Generator().manual_seed(77)
+    b, f, hh, ww, heads, c = 2, 24, 8, 4, 2, 64
+    p, hid = hh * ww, heads * 32
+    x = torch.randn(b * f, c, hh, ww, generator=g)
+    wq = torch.randn(3 * hid, c, 1, 1, generator=g) / 8
+    bias = torch.randn(heads, f, f, generator=g)
+    freqs = O.rotary_freqs(32)
+    ang = torch.outer(torch.arange(f).float(), freqs)
+    cos, sin = ang.cos().contiguous().to(dev()), ang.sin().contiguous().to(dev())
+    layer = ConvLayer(wq.to(dev()), None, pad=0)
+    qkv = f32(b * f * p, 3 * hid, dev())
+    layer([make_sb(rows_of(x))], b * f, hh, ww, out_f32=qkv, rot=(cos, sin, f, p, 2 * hid, hid, 32 ** -0.5))
+    assert layer.rot_applied and layer.last_engine == "tc"
+    y = rows_of(F.conv2d(x, wq)).reshape(b, f, p, 3 * hid)                  # rows (b, f, p)
+    q, k, v = [t.reshape(b, f, p, heads, 32).permute(0, 2, 3, 1, 4) for t in y.chunk(3, -1)]   # (b, p, h, f, d)
+    q = O.rotary_apply(q * 32 ** -0.5, freqs)
+    k = O.rotary_apply(k, freqs)
+    back = lambda t: t.permute(0, 3, 1, 2, 4).reshape(b * f * p, hid)
+    close(qkv, torch.cat([back(q), back(k), back(v)], 1), "qkv with fused rotary")
+    sim = torch.einsum("...id,...jd->...ij", q, k) + bias[None, None]
+    att = (sim - sim.amax(-1, keepdim=True)).softmax(-1)
+    ref = back(torch.einsum("...ij,...jd->...id", att, v))
+    out = torch.empty(b * f * p, hid, device=dev())
+    ops.attn_softmax_pre(qkv, None, out, b * p, f, heads, p, f * p, 1, p, bias.to(dev()))
+    close(out, ref, "attention on pre-rotated q|k")
+
+
 @pytest.mark.parametrize("f", [17, 24, 33, 39])
 def test_attn_temporal_ragged_lengths(f):
     """rotary + bias on frame counts that leave partial 16-row query tiles / odd bias rows (ldmatrix kernel, 17 <= L <= 40)"""
