@@ -674,14 +674,16 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
 // byte offset of 16-byte chunk `chunk` (8 dims) of row `row` inside a swizzled plane
 __device__ __forceinline__ int kv_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 
+template <bool FULL>      // FULL: seq_len == 40 (the 40-frame production case): every length test folds away
 __global__ void __launch_bounds__(128, 4) attn_softmax_mma16v2_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
                                                                       int64_t out_plane, float* __restrict__ out_f32,
-                                                                      int64_t n_seq, int L, int heads, int64_t inner,
+                                                                      int64_t n_seq, int L_arg, int heads, int64_t inner,
                                                                       int64_t outer_stride, int64_t inner_stride,
                                                                       int64_t row_stride, const float* __restrict__ rot_cos,
                                                                       const float* __restrict__ rot_sin,
                                                                       const float* __restrict__ pos_bias, int q_prescaled) {
     pdl_prologue_done();
+    const int L = FULL ? ML : L_arg;
     extern __shared__ __align__(16) uint8_t s_dyn2[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t unit = (int64_t)blockIdx.x * 4 + w;
@@ -742,9 +744,9 @@ __global__ void __launch_bounds__(128, 4) attn_softmax_mma16v2_kernel(const floa
             const int idx = lane + 32 * i, j = idx >> 3, c4 = idx & 7;
             float4 v = kr[i];
             if (rot_cos && j < L) {
-                const float c0 = rot_cos[j * (DH / 2) + 2 * c4], s0 = rot_sin[j * (DH / 2) + 2 * c4];
-                const float c1 = rot_cos[j * (DH / 2) + 2 * c4 + 1], s1 = rot_sin[j * (DH / 2) + 2 * c4 + 1];
-                v = make_float4(v.x * c0 - v.y * s0, v.y * c0 + v.x * s0, v.z * c1 - v.w * s1, v.w * c1 + v.z * s1);
+                const float2 cc = *reinterpret_cast<const float2*>(rot_cos + j * (DH / 2) + 2 * c4);   // pairs 2 c4, 2 c4 + 1
+                const float2 sn = *reinterpret_cast<const float2*>(rot_sin + j * (DH / 2) + 2 * c4);
+                v = make_float4(v.x * cc.x - v.y * sn.x, v.y * cc.x + v.x * sn.x, v.z * cc.y - v.w * sn.y, v.w * cc.y + v.z * sn.y);
             }
             uint2 hv, lv;
             split_bf16x2(v.x, v.y, hv.x, lv.x);
@@ -831,6 +833,8 @@ __global__ void __launch_bounds__(128, 4) attn_softmax_mma16v2_kernel(const floa
         for (int half = 0; half < 2; ++half) {
             const int i = half ? i1 : i0;
             const bool row_ok = i < L;
+            if (!row_ok) continue;                 // rows >= L of the last tile: never stored, their P fragments only feed dead O rows
+            const unsigned gmask = 0xFu << (lane & ~3);    // the 4 lanes that share this row (row_ok is uniform inside the group)
             float mx = -INFINITY;
 #pragma unroll
             for (int nt = 0; nt < 5; ++nt) {
@@ -848,8 +852,8 @@ __global__ void __launch_bounds__(128, 4) attn_softmax_mma16v2_kernel(const floa
                     mx = fmaxf(mx, v);
                 }
             }
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, 2));
             float sum = 0.f;
 #pragma unroll
             for (int nt = 0; nt < 5; ++nt)
@@ -859,8 +863,8 @@ __global__ void __launch_bounds__(128, 4) attn_softmax_mma16v2_kernel(const floa
                     acc[nt][2 * half + e] = ex;
                     sum += ex;
                 }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            sum += __shfl_xor_sync(gmask, sum, 1);
+            sum += __shfl_xor_sync(gmask, sum, 2);
             const float inv = 1.f / sum;
 #pragma unroll
             for (int nt = 0; nt < 5; ++nt) { acc[nt][2 * half] *= inv; acc[nt][2 * half + 1] *= inv; }
@@ -924,6 +928,17 @@ __global__ void __launch_bounds__(128, 4) attn_softmax_mma16v2_kernel(const floa
         }
         __syncwarp();
     }
+}
+
+inline int v2_set_smem(size_t smem) {
+    static bool done = false;
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(attn_softmax_mma16v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_softmax_mma16v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        done = true;
+    }
+    return 0;
 }
 
 // one block (4 warps) per (frame, head).  Every warp streams 32-row chunks of (k, v) and later q through a
@@ -1292,16 +1307,17 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
         static const bool use_v1 = (getenv("LFDM_ATTN_V1") != nullptr);          // A/B switch: first mma.m16n8k16 kernel
         if (use_mma && !use_tf32 && !use_v1 && seq_len >= 17) {
             const size_t smem = (size_t)4 * V2_WARP_BYTES;
-            static bool attr2 = false;
-            if (!attr2) {
-                cudaError_t e = cudaFuncSetAttribute(attn_softmax_mma16v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return (int)e;
-                attr2 = true;
-            }
+            int rc = v2_set_smem(smem);
+            if (rc) return rc;
             const int64_t units = n_seq * heads;
-            LFDM_LAUNCH_PDL(attn_softmax_mma16v2_kernel, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
-                            qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
-                            row_stride, rot_cos, rot_sin, pos_bias, 0);
+            if (seq_len == ML)
+                LFDM_LAUNCH_PDL(attn_softmax_mma16v2_kernel<true>, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
+                                qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
+                                row_stride, rot_cos, rot_sin, pos_bias, 0);
+            else
+                LFDM_LAUNCH_PDL(attn_softmax_mma16v2_kernel<false>, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
+                                qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
+                                row_stride, rot_cos, rot_sin, pos_bias, 0);
             return 0;
         }
         if (use_mma && !use_tf32) {
@@ -1346,12 +1362,17 @@ extern "C" int lfdm_attn_softmax_pre(const float* qkv, void* out_sb, int64_t out
     if (seq_len < 17 || seq_len > ML) return LFDM_E_UNSUPP;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)4 * V2_WARP_BYTES;
-    cudaError_t e = cudaFuncSetAttribute(attn_softmax_mma16v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    int rc = v2_set_smem(smem);
+    if (rc) return rc;
     const int64_t units = n_seq * heads;
-    LFDM_LAUNCH_PDL(attn_softmax_mma16v2_kernel, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
-                    qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
-                    row_stride, (const float*)nullptr, (const float*)nullptr, pos_bias, 1);
+    if (seq_len == ML)
+        LFDM_LAUNCH_PDL(attn_softmax_mma16v2_kernel<true>, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
+                        qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
+                        row_stride, (const float*)nullptr, (const float*)nullptr, pos_bias, 1);
+    else
+        LFDM_LAUNCH_PDL(attn_softmax_mma16v2_kernel<false>, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
+                        qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
+                        row_stride, (const float*)nullptr, (const float*)nullptr, pos_bias, 1);
     return 0;
 }
 
