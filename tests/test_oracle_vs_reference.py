@@ -26,6 +26,22 @@ def test_oracle_matches_reference_tiny(ns):
             assert torch.equal(ref, mine)
 
 
+def test_oracle_matches_reference_natops_style(ns):
+    """nearest-upsample + reflect-padded 3x3 conv instead of ConvTranspose, learned null condition (NATOPS options,
+    video_flow_diffusion.py:156-163,395-399): oracle == unmodified reference, bit for bit"""
+    from oracle import lfdm_oracle as O
+    from oracle.make_golden import TINY_UNET
+    torch.manual_seed(5)
+    cfg = dict(TINY_UNET, use_deconv=False, padding_mode="reflect", learn_null_cond=True)
+    unet = ns.Unet3D(**cfg).eval()
+    x, t, cond = torch.randn(2, 11, 5, 8, 8), torch.tensor([500, 7]), torch.randn(2, 24)
+    with torch.no_grad():
+        for cs in (1.0, 2.0):
+            ref = unet.forward_with_cond_scale(x, t, cond=cond, cond_scale=cs)
+            mine = O.unet3d_forward_with_cond_scale(unet.state_dict(), x, t, cond, cs, heads=2, padding_mode="reflect")
+            assert torch.equal(ref, mine)
+
+
 def test_state_dict_and_init_identity(ns):
     """same seed -> bit-identical parameters & key order as the reference (drop-in checkpoints, seeded goldens)"""
     import cvpr23_lfdm_b200 as P
