@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) unet_heads_kernel(const float* __restrict
                                                          const float* __restrict__ ba, int na,
                                                          const float* __restrict__ o, const float* __restrict__ wo,
                                                          const float* __restrict__ bo, int no, int c, int f, int p,
-                                                         int64_t m_total, float* __restrict__ out) {
+                                                         int64_t m_total, float* __restrict__ out, int64_t null_off, float cfg) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -230,6 +230,13 @@ __global__ void __launch_bounds__(256) unet_heads_kernel(const float* __restrict
             float acc = 0.f;
             for (int k = lane; k < c; k += 32) acc = fmaf(src[m * c + k], wv[k], acc);
             acc = warp_sum(acc);
+            if (null_off) {          // classifier-free guidance: rows m (cond) and m + null_off (null) of a 2B batch
+                float accn = 0.f;
+                for (int k = lane; k < c; k += 32) accn = fmaf(src[(m + null_off) * c + k], wv[k], accn);
+                accn = warp_sum(accn);
+                const float bb = ch < na ? (ba ? ba[ch] : 0.f) : (bo ? bo[ch - na] : 0.f);
+                acc = (accn + bb) + ((acc + bb) - (accn + bb)) * cfg - bb;
+            }
             if (lane == 0) {
                 float bias = ch < na ? (ba ? ba[ch] : 0.f) : (bo ? bo[ch - na] : 0.f);
                 out[(((int64_t)bi * nch + ch) * f + fi) * p + pp] = acc + bias;
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(256) unet_heads64_kernel(const float* __restri
                                                            const float* __restrict__ ba, int na,
                                                            const float* __restrict__ o, const float* __restrict__ wo,
                                                            const float* __restrict__ bo, int no, int f, int p,
-                                                           int64_t m_total, float* __restrict__ out) {
+                                                           int64_t m_total, float* __restrict__ out, int64_t null_off, float cfg) {
     pdl_prologue_done();
     const int lane = threadIdx.x & 31, sub = lane & 7, rsel = lane >> 3;
     const int nch = na + no;
@@ -278,20 +285,41 @@ __global__ void __launch_bounds__(256) unet_heads64_kernel(const float* __restri
             for (int j = 0; j < 8; ++j) acc[ch] = fmaf(ch < na ? av[j] : ov[j], w[ch][j], acc[ch]);
         }
         const unsigned gmask = 0xffu << (rsel * 8);
+        if (null_off) {              // classifier-free guidance (reference :521-526): eps = null + (cond - null) * scale, with
+                                     // logits - null_logits formed first as the reference does; rows m / m + null_off of a 2B batch
+            const int64_t mn = m + null_off;
+            const float4 c0 = *reinterpret_cast<const float4*>(a + mn * 64 + sub * 8), c1 = *reinterpret_cast<const float4*>(a + mn * 64 + sub * 8 + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(o + mn * 64 + sub * 8), d1 = *reinterpret_cast<const float4*>(o + mn * 64 + sub * 8 + 4);
+            const float an[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            const float on[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                float accn = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) accn = fmaf(ch < na ? an[j] : on[j], w[ch][j], accn);
+                acc[ch] += __shfl_xor_sync(gmask, acc[ch], 1); accn += __shfl_xor_sync(gmask, accn, 1);
+                acc[ch] += __shfl_xor_sync(gmask, acc[ch], 2); accn += __shfl_xor_sync(gmask, accn, 2);
+                acc[ch] += __shfl_xor_sync(gmask, acc[ch], 4); accn += __shfl_xor_sync(gmask, accn, 4);
+                const float lc = acc[ch] + bias[ch], ln = accn + bias[ch];
+                acc[ch] = ln + (lc - ln) * cfg;                 // bias already inside both logits
+            }
+        } else {
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
             acc[ch] += __shfl_xor_sync(gmask, acc[ch], 1);
             acc[ch] += __shfl_xor_sync(gmask, acc[ch], 2);
             acc[ch] += __shfl_xor_sync(gmask, acc[ch], 4);
         }
+        }
         if (sub < nch) {
             const int64_t n = m / p;
             const int pp = (int)(m - n * p);
             const int bi = (int)(n / f), fi = (int)(n - (int64_t)bi * f);
-            float v = acc[0] + bias[0];
-            if (sub == 1) v = acc[1] + bias[1];
-            if (sub == 2) v = acc[2] + bias[2];
-            if (sub == 3) v = acc[3] + bias[3];
+            const float bz = null_off ? 0.f : 1.f;
+            float v = acc[0] + bz * bias[0];
+            if (sub == 1) v = acc[1] + bz * bias[1];
+            if (sub == 2) v = acc[2] + bz * bias[2];
+            if (sub == 3) v = acc[3] + bz * bias[3];
             out[(((int64_t)bi * nch + sub) * f + fi) * p + pp] = v;
         }
     }
@@ -385,9 +413,9 @@ extern "C" int lfdm_avgpool2_rows(const float* in, int n, int h, int w, int c, f
     return 0;
 }
 
-extern "C" int lfdm_unet_heads(const float* a, const float* wa, const float* ba, int na, const float* o,
-                               const float* wo, const float* bo, int no, int c, int b, int f, int p, float* out,
-                               void* stream) {
+static int unet_heads_launch(const float* a, const float* wa, const float* ba, int na, const float* o, const float* wo,
+                             const float* bo, int no, int c, int b, int f, int p, float* out, int64_t null_off, float cfg,
+                             void* stream) {
     if (!a || !o || !wa || !wo || !out) return LFDM_E_BADARG;
     int64_t m = (int64_t)b * f * p;
     int64_t blocks = (m + 7) / 8;
@@ -396,11 +424,24 @@ extern "C" int lfdm_unet_heads(const float* a, const float* wa, const float* ba,
                                                          reinterpret_cast<uintptr_t>(wa) | reinterpret_cast<uintptr_t>(wo)) & 15) == 0) {
         int64_t b4 = (m + 31) / 32;            // 8 warps x 4 rows per pass
         if (b4 > 148 * 8) b4 = 148 * 8;
-        LFDM_LAUNCH_PDL(unet_heads64_kernel, dim3((unsigned)b4), dim3(256), 0, (cudaStream_t)stream, a, wa, ba, na, o, wo, bo, no, f, p, m, out);
+        LFDM_LAUNCH_PDL(unet_heads64_kernel, dim3((unsigned)b4), dim3(256), 0, (cudaStream_t)stream, a, wa, ba, na, o, wo, bo, no, f, p, m, out, null_off, cfg);
     } else
-    unet_heads_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, wa, ba, na, o, wo, bo, no, c, f, p, m, out);
+    unet_heads_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, wa, ba, na, o, wo, bo, no, c, f, p, m, out, null_off, cfg);
     LFDM_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int lfdm_unet_heads(const float* a, const float* wa, const float* ba, int na, const float* o,
+                               const float* wo, const float* bo, int no, int c, int b, int f, int p, float* out,
+                               void* stream) {
+    return unet_heads_launch(a, wa, ba, na, o, wo, bo, no, c, b, f, p, out, 0, 1.f, stream);
+}
+
+extern "C" int lfdm_unet_heads_cfg(const float* a, const float* wa, const float* ba, int na, const float* o,
+                                   const float* wo, const float* bo, int no, int c, int b, int f, int p, float cond_scale,
+                                   float* out, void* stream) {
+    if (b < 1) return LFDM_E_BADARG;
+    return unet_heads_launch(a, wa, ba, na, o, wo, bo, no, c, b, f, p, out, (int64_t)b * f * p, cond_scale, stream);
 }
 
 extern "C" int lfdm_split_bf16(const float* in, void* out_sb, int64_t out_plane, int64_t n, void* stream) {

@@ -236,15 +236,28 @@ class Unet3D(nn.Module):
         return super().load_state_dict(*a, **k)
 
     # ---- reference API ---------------------------------------------------------------
+    @torch.no_grad()
     def forward_with_cond_scale(self, *args, cond_scale=2., **kwargs):
-        """reference :511-526"""
+        """reference :511-526.  cond_scale == 0: null-condition forward only; == 1 (or no cond): one conditional forward;
+        otherwise null + (cond - null) * cond_scale -- evaluated here as ONE 2B batch [cond ; null] through the engine with the
+        combination fused into the head kernel (the reference runs two forwards; results agree to fp32 rounding)."""
         if cond_scale == 0:
             return self.forward(*args, null_cond_prob=1., **kwargs)
-        logits = self.forward(*args, null_cond_prob=0., **kwargs)
         if cond_scale == 1 or not self.has_cond:
-            return logits
-        null_logits = self.forward(*args, null_cond_prob=1., **kwargs)
-        return null_logits + (logits - null_logits) * cond_scale
+            return self.forward(*args, null_cond_prob=0., **kwargs)
+        plain = set(kwargs) <= {"cond"} and len(args) <= 3
+        if not plain:       # exotic keyword use (none_cond_mask ...): literal two-pass form
+            logits = self.forward(*args, null_cond_prob=0., **kwargs)
+            null_logits = self.forward(*args, null_cond_prob=1., **kwargs)
+            return null_logits + (logits - null_logits) * cond_scale
+        x, time = args[0], args[1]
+        cond = args[2] if len(args) > 2 else kwargs.get("cond")
+        assert exists(cond), 'cond must be passed in if cond_dim specified'
+        b = x.shape[0]
+        null = self.null_cond_emb.to(x.device).float().expand(b, -1)
+        self.null_cond_mask = torch.ones((b,), device=x.device, dtype=torch.bool)     # state after the reference's second pass
+        return self.engine().forward(torch.cat([x, x], 0), torch.cat([time, time], 0),
+                                     torch.cat([cond.to(x.device).float(), null], 0), cfg_scale=float(cond_scale))
 
     @torch.no_grad()
     def forward(self, x, time, cond=None, null_cond_prob=0., none_cond_mask=None, focus_present_mask=None,

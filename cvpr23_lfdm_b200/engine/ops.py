@@ -225,6 +225,46 @@ def attn_linear(qkv, out_sb, out_f32, n_frames, n_pos, heads):
                                  stream()), "lfdm_attn_linear")
 
 
+def _sw128_image(rows_bf16):
+    """(R, 64) bf16 rows of 128 bytes -> the kernel's shared-memory image: 16-byte chunk c of row r stored at chunk
+    c ^ (r & 7) (the 128-byte swizzle of the UMMA / TMA operand layout; 8-row groups are contiguous 1024-byte atoms)."""
+    r = rows_bf16.shape[0]
+    assert rows_bf16.shape[1] == 64 and r % 8 == 0
+    ch = rows_bf16.reshape(r, 8, 8)
+    idx = torch.arange(8, device=rows_bf16.device)[None, :] ^ (torch.arange(r, device=rows_bf16.device)[:, None] & 7)   # (r, 8)
+    return torch.gather(ch, 1, idx[:, :, None].expand(r, 8, 8)).reshape(r, 64).contiguous()     # out[r, c'] = in[r, c' ^ (r&7)]
+
+
+def pack_fused_attention(qkv_w, out_w, heads):
+    """to_qkv weight (3*hid, 64) and to_out weight (64, hid) -> per-head split-bf16 operand images of
+    lfdm_attn_temporal_fused (include/lfdm_b200.h): (heads, 2, 96, 64) and (heads, 64, 64) bf16."""
+    hid = heads * 32
+    qkv_w = qkv_w.detach().float().reshape(3 * hid, -1)
+    out_w = out_w.detach().float().reshape(-1, hid)
+    assert qkv_w.shape[1] == 64 and out_w.shape[0] == 64
+    wq, wo = [], []
+    for h in range(heads):
+        wh = torch.cat([qkv_w[h * 32:(h + 1) * 32], qkv_w[hid + h * 32:hid + (h + 1) * 32],
+                        qkv_w[2 * hid + h * 32:2 * hid + (h + 1) * 32]], 0)                   # (96, 64): q_h; k_h; v_h
+        pl = split_planes(wh)                                                                  # (2, 96, 64)
+        wq.append(torch.stack([_sw128_image(pl[0]), _sw128_image(pl[1])], 0))
+        oh = split_planes(out_w[:, h * 32:(h + 1) * 32])                                       # (2, 64, 32)
+        wo.append(_sw128_image(torch.cat([oh[0], oh[1]], 1)))                                  # rows [w_hi(32) | w_lo(32)]
+    return torch.stack(wq, 0).contiguous(), torch.stack(wo, 0).contiguous()
+
+
+def attn_temporal_fused(x, gamma, wq, wo, out_bias, cos, sin, pos_bias, out_f32, out_sb, n_b, frames, pixels, heads, eps,
+                        debug=None):
+    """returns the C-ABI code (0, or L.E_UNSUPP when the geometry is not covered by the fused kernel)"""
+    rc = lib().lfdm_attn_temporal_fused(ptr(x), ptr(gamma), ptr(wq), ptr(wo), ptr(out_bias), ptr(cos), ptr(sin), ptr(pos_bias),
+                                        ptr(out_f32), ptr(out_sb.t) if out_sb is not None else None,
+                                        out_sb.plane if out_sb is not None else 0, n_b, frames, pixels, x.shape[1], heads,
+                                        eps, ptr(debug), stream())
+    if rc != L.E_UNSUPP:
+        check(rc, "lfdm_attn_temporal_fused")
+    return rc
+
+
 def small_linear(x, w, b, y, act_in=0, act_out=0):
     rows, k = x.shape
     n = w.shape[0]

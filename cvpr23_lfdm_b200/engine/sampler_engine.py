@@ -20,19 +20,27 @@ class SamplerEngine:
         self.device = gd.betas.device
         if self.device.type != "cuda":
             raise RuntimeError("cvpr23_lfdm_b200.GaussianDiffusion samples only on a CUDA (sm_100a) device; no CPU fallback")
-        self._graphs = {}
+        self._coef_cache = {}
+        self._loops = {}      # (engine, shape, guided, steps) -> persistent buffers + captured step graph
 
-    # ---- per-step coefficient tables (float32 torch arithmetic on the registered buffers, as the reference does) ----
+    # ---- per-step coefficient tables (float32 torch arithmetic on the registered buffers, as the reference does; built
+    # ---- vectorised over all steps and cached: they only depend on the schedule buffers) --------------------------------
+    def _buf_key(self):
+        g = self.gd
+        return (g.betas._version, g.betas.data_ptr(), g.sampling_timesteps, float(g.ddim_sampling_eta))
+
     def _ddpm_rows(self, ts, clip=True):
         g = self.gd
-        rows = []
-        for t in ts:
-            sigma = (0.5 * g.posterior_log_variance_clipped[t]).exp() * (0.0 if t == 0 else 1.0)
-            rows.append(torch.stack([g.sqrt_recip_alphas_cumprod[t], g.sqrt_recipm1_alphas_cumprod[t],
-                                     g.posterior_mean_coef1[t], g.posterior_mean_coef2[t], sigma,
-                                     torch.zeros_like(sigma), torch.zeros_like(sigma),
-                                     torch.full_like(sigma, 0.0 if clip else 1.0)]))
-        return torch.stack(rows).contiguous()
+        key = ("ddpm", tuple(ts), bool(clip)) + self._buf_key()
+        hit = self._coef_cache.get(key)
+        if hit is not None:
+            return hit
+        t = torch.tensor(list(ts), device=self.device, dtype=torch.long)
+        sigma = (0.5 * g.posterior_log_variance_clipped[t]).exp() * (t != 0).to(torch.float32)
+        z = torch.zeros_like(sigma)
+        rows = torch.stack([g.sqrt_recip_alphas_cumprod[t], g.sqrt_recipm1_alphas_cumprod[t], g.posterior_mean_coef1[t],
+                            g.posterior_mean_coef2[t], sigma, z, z, torch.full_like(sigma, 0.0 if clip else 1.0)], 1).contiguous()
+        return self._remember(key, rows)
 
     def _ddim_pairs(self):
         g = self.gd
@@ -42,17 +50,26 @@ class SamplerEngine:
 
     def _ddim_rows(self, pairs, clip=True):
         g = self.gd
+        key = ("ddim", tuple(pairs), bool(clip)) + self._buf_key()
+        hit = self._coef_cache.get(key)
+        if hit is not None:
+            return hit
         eta = g.ddim_sampling_eta
-        rows = []
-        for time, time_next in pairs:
-            alpha = g.alphas_cumprod_prev[time]
-            alpha_next = g.alphas_cumprod_prev[time_next]
-            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
-            c = ((1 - alpha_next) - sigma ** 2).sqrt()
-            rows.append(torch.stack([g.sqrt_recip_alphas_cumprod[time], g.sqrt_recipm1_alphas_cumprod[time],
-                                     alpha_next.sqrt(), torch.zeros_like(c), sigma, c, torch.ones_like(c),
-                                     torch.full_like(c, 0.0 if clip else 1.0)]))
-        return torch.stack(rows).contiguous()
+        t0 = torch.tensor([p[0] for p in pairs], device=self.device, dtype=torch.long)
+        t1 = torch.tensor([p[1] for p in pairs], device=self.device, dtype=torch.long)
+        alpha, alpha_next = g.alphas_cumprod_prev[t0], g.alphas_cumprod_prev[t1]
+        sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+        c = ((1 - alpha_next) - sigma ** 2).sqrt()
+        rows = torch.stack([g.sqrt_recip_alphas_cumprod[t0], g.sqrt_recipm1_alphas_cumprod[t0], alpha_next.sqrt(),
+                            torch.zeros_like(c), sigma, c, torch.ones_like(c), torch.full_like(c, 0.0 if clip else 1.0)],
+                           1).contiguous()
+        return self._remember(key, rows)
+
+    def _remember(self, key, rows):
+        if len(self._coef_cache) >= 8:
+            self._coef_cache.clear()
+        self._coef_cache[key] = rows
+        return rows
 
     def _rank(self, n):
         r = torch.tensor(self.gd.dynamic_thres_percentile, dtype=torch.float32) * (n - 1)   # at::quantile rank (fp32)
@@ -110,13 +127,17 @@ class SamplerEngine:
 
     # ---- the hot loops -------------------------------------------------------------------------------------------
     def _run_loop(self, fea, shape, cond, cond_scale, coef, times, draw_noise, clip_denoised=True):
-        """times: python list of UNet timesteps per step; draw_noise[i]: whether step i consumes a noise draw."""
+        """times: python list of UNet timesteps per step; draw_noise[i]: whether step i consumes a noise draw.
+
+        Everything a step reads lives in persistent device buffers (image, noise, hoisted init-conv term, (scale, shift)
+        tables, coefficient table, step counter) kept per (engine, shape, guided, schedule): a repeated `sample()` call
+        refills them and replays the step graph captured by the first call instead of rebuilding tables and re-capturing."""
         g = self.gd
         dev = self.device
         unet = g.denoise_fn
         b = shape[0]
-        img = g._randn(shape, dev).contiguous()
         if not hasattr(unet, "engine"):       # foreign denoiser: plain reference data flow, our sampler kernels
+            img = g._randn(shape, dev).contiguous()
             for i, t in enumerate(times):
                 tt = torch.full((b,), t, device=dev, dtype=torch.long)
                 eps = self._eps_generic(img, tt, fea, cond, cond_scale).contiguous()
@@ -124,60 +145,88 @@ class SamplerEngine:
                 self._update(img, eps, noise, coef[i:i + 1].contiguous(), None, False, img, clip_denoised)
             return img
         eng = unet.engine()
+        n = len(times)
+        guided = bool(unet.has_cond) and cond_scale not in (0, 1)      # reference :515-526: 0 -> null only, 1 -> cond only
+        null_only = bool(unet.has_cond) and cond_scale == 0
+        key = (id(eng), tuple(shape), guided, float(cond_scale) if guided else 1.0, tuple(times), tuple(draw_noise),
+               bool(clip_denoised), coef.data_ptr())
+        st = self._loops.get(key)
+        if st is None or st["eng"] is not eng:
+            if len(self._loops) >= 2:           # each entry pins one step's activation pool: keep at most two
+                self._loops.clear()
+            st = {"eng": eng, "graph": None, "img": torch.empty(shape, device=dev), "noise": torch.empty(shape, device=dev),
+                  "step_idx": torch.zeros((1,), dtype=torch.int32, device=dev), "fea_conv": None, "cond_tab": None,
+                  "x2": torch.empty((2 * b,) + tuple(shape[1:]), device=dev) if guided else None}
+            self._loops[key] = st
+        img, noise_buf, step_idx = st["img"], st["noise"], st["step_idx"]
+        img.copy_(g._randn(shape, dev))
+        step_idx.zero_()
+        # ---- per-call inputs into the persistent buffers
         fea_conv = eng.prepare_fea(fea)
-        tvec = torch.tensor(times, device=dev, dtype=torch.long)
         if cond is not None:
             cond = cond.to(dev).float()
-        guided = not (cond_scale == 1 or not unet.has_cond)
-        null_only = cond_scale == 0 and unet.has_cond
         null_emb = unet.null_cond_emb.detach().to(dev).float().expand(b, -1).contiguous() if unet.has_cond else None
-        tabs = eng.build_tables(tvec, null_emb if null_only else cond)
-        tabs_null = eng.build_tables(tvec, null_emb) if guided else None
-        step_idx = torch.zeros((1,), dtype=torch.int32, device=dev)
+        tvec = torch.tensor(times, device=dev, dtype=torch.long)
+        time_tab, cond_tab = eng.build_tables(tvec, null_emb if null_only else cond)
+        if guided:                               # one 2B batch: [conditional half ; null-condition half]
+            _, null_tab = eng.build_tables(tvec, null_emb)
+            cond_tab = torch.cat([cond_tab.expand(b, -1), null_tab.expand(b, -1)], 0)
+            fea_conv = torch.cat([fea_conv, fea_conv], 0)
+        for name, val in (("fea_conv", fea_conv), ("cond_tab", cond_tab.contiguous())):
+            if st[name] is None or st[name].shape != val.shape:
+                st[name] = val.clone()
+                st["graph"] = None
+            else:
+                st[name].copy_(val)
+        if st.get("time_tab") is not time_tab:  # cached inside the engine: same tensor for the same schedule
+            st["time_tab"] = time_tab
+            st["graph"] = None
+        fea_conv, cond_tab = st["fea_conv"], st["cond_tab"]
+        bb = 2 * b if guided else b
 
         def step(noise):
-            ss = eng.ss_from_tables(tabs[0], tabs[1], step_idx, b)
-            eps = eng.forward_hoisted(img, fea_conv, ss)
+            ss = eng.ss_from_tables(time_tab, cond_tab, step_idx, bb)
             if guided:
-                ssn = eng.ss_from_tables(tabs_null[0], tabs_null[1], step_idx, b)
-                eps_null = eng.forward_hoisted(img, fea_conv, ssn)
-                eps = eps_null + (eps - eps_null) * cond_scale      # reference :526
+                x2 = st["x2"]
+                x2[:b].copy_(img)
+                x2[b:].copy_(img)
+                eps = eng.forward_hoisted(x2, fea_conv, ss, cfg_scale=float(cond_scale))
+            else:
+                eps = eng.forward_hoisted(img, fea_conv, ss)
             self._update(img, eps, noise, coef, step_idx, True, img, clip_denoised)
 
         graphable = USE_GRAPH and g.noise_fn is None
-        n = len(times)
         i = 0
-        calls0 = L.launch_count
-        self.last_stats = {"steps": n, "calls_per_step": 0, "other_calls": 0}
+        self.last_stats = {"steps": n, "calls_per_step": st.get("calls_per_step", 0), "other_calls": 0,
+                           "graph_reused": st["graph"] is not None}
         if graphable and n >= 4:
-            # leading steps run eagerly (also warms every kernel / allocator pool), then one graph per noise pattern
-            noise_buf = torch.empty(shape, device=dev)
-            while i < 2:
-                c0 = L.launch_count
-                step(g._randn(shape, dev) if draw_noise[i] else None)
-                self.last_stats["calls_per_step"] = L.launch_count - c0
-                i += 1
-            graph = None
+            if st["graph"] is None:
+                # leading steps run eagerly (also warms every kernel / allocator pool), then the step is captured once
+                while i < 2:
+                    c0 = L.launch_count
+                    step(g._randn(shape, dev) if draw_noise[i] else None)
+                    st["calls_per_step"] = self.last_stats["calls_per_step"] = L.launch_count - c0
+                    i += 1
             while i < n:
                 if draw_noise[i]:
-                    if graph is None:
+                    if st["graph"] is None:
                         torch.cuda.synchronize()
                         graph = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(graph):
                             noise_buf.normal_()
                             step(noise_buf)
-                        # capture does not execute: replay for this step
-                    graph.replay()
+                        st["graph"] = graph         # capture does not execute: replay for this step
+                    st["graph"].replay()
                 else:
                     step(None)
                 i += 1
-            return img
+            return img.clone()
         while i < n:
             c0 = L.launch_count
             step(g._randn(shape, dev) if draw_noise[i] else None)
             self.last_stats["calls_per_step"] = L.launch_count - c0
             i += 1
-        return img
+        return img.clone()
 
     def p_sample_loop(self, fea, shape, cond=None, cond_scale=1.):
         g = self.gd

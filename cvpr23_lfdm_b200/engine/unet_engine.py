@@ -21,6 +21,9 @@ from .ops import ConvLayer, f32
 # moves ~0.1 ms per 32x32 call from the attention kernel (16 warps/SM) into the 8 epilogue warps of an HBM-bound GEMM
 # and loses overall (conv 6.45 -> 6.83 ms per evaluation).
 FUSE_ROTARY = os.environ.get("LFDM_FUSED_ROTARY") is not None
+# LFDM_FUSED_ATTN=0: compose the temporal-attention block from layernorm / qkv conv / attention core / out conv instead
+# of the single tcgen05 kernel lfdm_attn_temporal_fused (C = 64, 40 frames) -- A/B switch and cross-check.
+FUSED_ATTN = os.environ.get("LFDM_FUSED_ATTN", "1") == "1"
 
 
 def _rel_pos_bucket(n, num_buckets=32, max_distance=32):
@@ -63,6 +66,10 @@ class _Attn:
         self.out = ConvLayer(out_w.detach().reshape(out_w.shape[0], -1, 1, 1), out_b, name=name + ".out")
         self.heads = heads
         self.hid = qkv_w.shape[0] // 3
+        self.out_bias = out_b.detach().float().contiguous() if out_b is not None else None
+        self.fused = None          # (wq, wo) operand images of the fused temporal block (C == 64)
+        if c == 64 and qkv_w.shape[0] == 3 * heads * 32:
+            self.fused = ops.pack_fused_attention(qkv_w, out_w, heads)
 
 
 class UnetEngine:
@@ -169,6 +176,7 @@ class UnetEngine:
         self.ss_w_time = self.ss_w[:, :self.time_dim].contiguous()
         self.ss_w_cond = self.ss_w[:, self.time_dim:].contiguous() if self.cond_dim else None
         self.taps = None   # optional dict filled with F32 copies of intermediate activations (debug / tests)
+        self._time_tab_cache = {}   # tuple(times) -> (len(times), ss_total) table: depends only on the weights of this engine
 
     # ------------------------------------------------------------------------------------------------
     # embeddings
@@ -197,9 +205,15 @@ class UnetEngine:
     def build_tables(self, times, cond):
         """hoisted form: time table (len(times), ss_total) and cond table (B, ss_total) with
         ss(step, b) = time_tab[step] + cond_tab[b]."""
-        t = self.time_embed(times)
-        time_tab = torch.empty((t.shape[0], self.ss_total), device=self.dev)
-        ops.small_linear(t, self.ss_w_time, None, time_tab, 1, 0)
+        key = tuple(int(v) for v in times.tolist())
+        time_tab = self._time_tab_cache.get(key)
+        if time_tab is None:
+            t = self.time_embed(times)
+            time_tab = torch.empty((t.shape[0], self.ss_total), device=self.dev)
+            ops.small_linear(t, self.ss_w_time, None, time_tab, 1, 0)
+            if len(self._time_tab_cache) >= 4:
+                self._time_tab_cache.clear()
+            self._time_tab_cache[key] = time_tab
         if self.cond_dim:
             cond_tab = torch.empty((cond.shape[0], self.ss_total), device=self.dev)
             ops.small_linear(cond.float().contiguous(), self.ss_w_cond, self.ss_b, cond_tab, 1, 0)
@@ -266,6 +280,14 @@ class UnetEngine:
     def _temporal(self, at, x_f32, b, f, h, w, want_sb):
         p = h * w
         bias, cos, sin = self._frame_tables(f)
+        if FUSED_ATTN and at.fused is not None:
+            m, c = x_f32.shape
+            out = f32(m, c, self.dev)
+            out_sb = SB(m, c, self.dev) if want_sb else None
+            rc = ops.attn_temporal_fused(x_f32, at.gamma, at.fused[0], at.fused[1], at.out_bias, cos, sin, bias, out, out_sb,
+                                         b, f, p, at.heads, at.eps)
+            if rc == 0:
+                return out, out_sb
         def core(qkv, o, pre=False):
             if pre:        # q*scale and the q / k rotary were applied by the qkv projection's epilogue
                 ops.attn_softmax_pre(qkv, o, None, b * p, f, at.heads, p, f * p, 1, p, bias)
@@ -322,8 +344,9 @@ class UnetEngine:
     # ------------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------------
-    def forward(self, x, time, cond):
-        """generic Unet3D.forward: x (B, channels, F, H, W) NCDHW fp32 -> (B, 3, F, H, W)"""
+    def forward(self, x, time, cond, cfg_scale=None):
+        """generic Unet3D.forward: x (B, channels, F, H, W) NCDHW fp32 -> (B, 3, F, H, W)
+        (cfg_scale: the batch is [cond half ; null half], see forward_hoisted)"""
         b, c, f, h, w = x.shape
         assert c == self.unet_channels
         ss = self.scale_shift(time, cond)
@@ -332,10 +355,12 @@ class UnetEngine:
         m = b * f * h * w
         x0, x0_sb = f32(m, self.init_dim, self.dev), SB(m, self.init_dim, self.dev)
         self.init_full([rows], b * f, h, w, out_f32=x0, out_sb=x0_sb)
-        return self._body(x0, x0_sb, ss, b, f, h, w)
+        return self._body(x0, x0_sb, ss, b, f, h, w, cfg_scale)
 
-    def forward_hoisted(self, x3, fea_conv, ss):
-        """x3 (B, 3, F, H, W); fea_conv from prepare_fea; ss (B, ss_total) -> (B, 3, F, H, W)"""
+    def forward_hoisted(self, x3, fea_conv, ss, cfg_scale=None):
+        """x3 (B, 3, F, H, W); fea_conv from prepare_fea; ss (B, ss_total) -> (B, 3, F, H, W).
+        cfg_scale: classifier-free guidance as ONE 2B batch (reference :521-526 runs two forwards): x3 / fea_conv / ss hold
+        [conditional half ; null-condition half]; the result is null + (cond - null) * cfg_scale of shape (B/2, 3, F, H, W)."""
         lx, lf, kpad, n_x = self._hoisted_layers()
         b, c, f, h, w = x3.shape
         m = b * f * h * w
@@ -344,7 +369,7 @@ class UnetEngine:
                                       cols.plane, stream()), "lfdm_im2col_small")
         x0, x0_sb = f32(m, self.init_dim, self.dev), SB(m, self.init_dim, self.dev)
         lx([cols], b * f, h, w, out_f32=x0, out_sb=x0_sb, residual=fea_conv, res_bcast_f=f)
-        return self._body(x0, x0_sb, ss, b, f, h, w)
+        return self._body(x0, x0_sb, ss, b, f, h, w, cfg_scale)
 
     def _next_stats(self, b, groups):
         """GroupNorm accumulators of one evaluation come from one pool zeroed by a single fill (not one per conv)"""
@@ -356,7 +381,7 @@ class UnetEngine:
         self._stats_off += n
         return t
 
-    def _body(self, r_f32, r_sb, ss, b, f, h, w):
+    def _body(self, r_f32, r_sb, ss, b, f, h, w, cfg_scale=None):
         nf = b * f
         self._stats_pool, self._stats_off = None, 0
         self._tap("init_conv", r_f32, b, f, h, w)
@@ -403,6 +428,13 @@ class UnetEngine:
         rps = f * h * w
         a, _ = self._resnet(self.head_a, [x_sb, r_sb], None, nf, h, w, rps, ss, b, want_sb=False)
         o, _ = self._resnet(self.head_o, [x_sb, r_sb], None, nf, h, w, rps, ss, b, want_sb=False)
+        if cfg_scale is not None:
+            assert b % 2 == 0
+            out = torch.empty((b // 2, self.out_grid_dim + self.out_conf_dim, f, h, w), device=self.dev)
+            check(lib().lfdm_unet_heads_cfg(ptr(a), ptr(self.wa), ptr(self.ba), self.out_grid_dim, ptr(o), ptr(self.wo),
+                                            ptr(self.bo), self.out_conf_dim, a.shape[1], b // 2, f, h * w, float(cfg_scale),
+                                            ptr(out), stream()), "lfdm_unet_heads_cfg")
+            return out
         out = torch.empty((b, self.out_grid_dim + self.out_conf_dim, f, h, w), device=self.dev)
         check(lib().lfdm_unet_heads(ptr(a), ptr(self.wa), ptr(self.ba), self.out_grid_dim, ptr(o), ptr(self.wo),
                                     ptr(self.bo), self.out_conf_dim, a.shape[1], b, f, h * w, ptr(out), stream()),

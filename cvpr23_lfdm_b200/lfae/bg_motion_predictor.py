@@ -1,7 +1,7 @@
 """Host-side mirror of reference LFAE/modules/bg_motion_predictor.py `BGMotionPredictor`."""
 import torch
 from torch import nn
-from .util import Encoder
+from .util import Encoder, module_state_key
 
 
 class BGMotionPredictor(nn.Module):
@@ -20,16 +20,14 @@ class BGMotionPredictor(nn.Module):
             self.fc.bias.data.copy_(torch.tensor(init, dtype=torch.float))
         self._eng = None
 
-    def _apply(self, fn, *a, **k):
-        self._eng = None
-        return super()._apply(fn, *a, **k)
-
     @torch.no_grad()
     def forward(self, source_image, driving_image):
         """reference bg_motion_predictor.py:42-57 -> (B,3,3)"""
         from ..engine.lfae_engine import BGPredictorEngine
         if source_image.device.type != "cuda":
             raise RuntimeError("BGMotionPredictor runs only on CUDA (sm_100a); no CPU fallback")
-        if self._eng is None:
+        key = module_state_key(self)
+        if self._eng is None or self._eng_key != key:      # rebuilt after load_state_dict / .to() / in-place updates
             self._eng = BGPredictorEngine(self)
+            self._eng_key = key
         return self._eng.forward(source_image, driving_image)

@@ -3,7 +3,7 @@ Same sub-module tree / state_dict keys / init order; compute_fea, forward_with_f
 run on the sm_100a kernels through `engine.lfae_engine.GeneratorEngine`."""
 import torch
 from torch import nn
-from .util import ResBlock2d, SameBlock2d, UpBlock2d, DownBlock2d
+from .util import ResBlock2d, SameBlock2d, UpBlock2d, DownBlock2d, module_state_key
 from .pixelwise_flow_predictor import PixelwiseFlowPredictor
 
 
@@ -32,22 +32,16 @@ class Generator(nn.Module):
         dev = self.final.weight.device
         if dev.type != "cuda":
             raise RuntimeError("cvpr23_lfdm_b200.Generator runs only on a CUDA (sm_100a) device; no CPU fallback")
-        if self._eng is None or self._eng.device != dev:
+        if self.training:
+            raise NotImplementedError(
+                "Generator is in train mode: batch-statistics BatchNorm is a training feature (out of scope); the "
+                "reference samples with the LFAE in eval mode (video_flow_diffusion_model.py:44,53,60, demo_mug.py:105). "
+                "Call .eval() first.")
+        key = module_state_key(self)
+        if self._eng is None or self._eng_key != key:
             self._eng = GeneratorEngine(self)
+            self._eng_key = key
         return self._eng
-
-    def _apply(self, fn, *a, **k):
-        self._eng = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._eng = None
-        return super().load_state_dict(*a, **k)
-
-    def train(self, mode=True):
-        if mode and self._eng is not None:
-            self._eng = None
-        return super().train(mode)
 
     @torch.no_grad()
     def compute_fea(self, source_image):

@@ -1,7 +1,7 @@
 """Host-side mirror of reference LFAE/modules/region_predictor.py `RegionPredictor`."""
 import torch
 from torch import nn
-from .util import Hourglass, AntiAliasInterpolation2d
+from .util import Hourglass, AntiAliasInterpolation2d, module_state_key
 
 
 class RegionPredictor(nn.Module):
@@ -23,16 +23,14 @@ class RegionPredictor(nn.Module):
             self.down = AntiAliasInterpolation2d(num_channels, self.scale_factor)
         self._eng = None
 
-    def _apply(self, fn, *a, **k):
-        self._eng = None
-        return super()._apply(fn, *a, **k)
-
     @torch.no_grad()
     def forward(self, x):
         """reference region_predictor.py:77-117 -> dict(shift, covar, heatmap, affine, u, d)"""
         from ..engine.lfae_engine import RegionPredictorEngine
         if x.device.type != "cuda":
             raise RuntimeError("RegionPredictor runs only on CUDA (sm_100a); no CPU fallback")
-        if self._eng is None:
+        key = module_state_key(self)
+        if self._eng is None or self._eng_key != key:      # rebuilt after load_state_dict / .to() / in-place updates
             self._eng = RegionPredictorEngine(self)
+            self._eng_key = key
         return self._eng.forward(x)

@@ -97,3 +97,12 @@ def make_coordinate_grid(spatial_size, type=None):
     y = 2 * (torch.arange(h).float() / (h - 1)) - 1
     g = torch.stack([x[None, :].repeat(h, 1), y[:, None].repeat(1, w)], 2)
     return g.type(type) if type is not None else g
+
+
+def module_state_key(mod):
+    """Identity of everything a packed engine was built from: device, version counter and storage of every parameter
+    AND buffer (BatchNorm running statistics are buffers).  In-place updates (`load_state_dict` through any parent
+    module, `copy_`, optimiser steps) bump `_version`; `.to()` / `.cuda()` change `data_ptr`.  Engines are rebuilt
+    when the key changes (same scheme as Unet3D.engine)."""
+    ts = list(mod.parameters()) + list(mod.buffers())
+    return tuple((t.device, t._version, t.data_ptr()) for t in ts)

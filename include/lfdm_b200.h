@@ -121,6 +121,19 @@ int lfdm_attn_softmax_pre(const float* qkv, void* out_sb, int64_t out_plane, flo
 int lfdm_attn_linear(const float* qkv, void* out_sb, int64_t out_plane, float* out_f32, int64_t n_frames, int n_pos,
                      int heads, void* stream);
 
+/* Whole temporal-attention block (Residual(PreNorm(EinopsToAndFrom(Attention))), video_flow_diffusion.py:132-138,
+ * 170-190,270-283,286-363) as ONE tcgen05 kernel: out = x + to_out(attention(to_qkv(LayerNorm(x)))) (+ out_bias).
+ * x / out rows [(b*frames + f)*pixels + p][c]; sequences run over f.  c == 64 and frames == 40 only (LFDM_E_UNSUPP
+ * otherwise: the caller then composes lfdm_layernorm / lfdm_conv / lfdm_attn_softmax).  wq_packed / wo_packed: per-head
+ * split-bf16 weight slices in the kernel's shared-memory image (heads x 24576 B: [hi|lo] planes of the 96 x 64 rows
+ * (q_h; k_h; v_h) of to_qkv; heads x 8192 B: 64 rows [w_hi(32) | w_lo(32)] of to_out[:, 32h:32h+32]), 128-byte rows
+ * with 16-byte chunk index XOR (row & 7) -- built once by the host (engine/ops.py: pack_fused_attention).
+ * debug: optional diagnostics [M][3*hid + heads*40 + hid] = rotated q | rotated k | v | softmax rows | head outputs. */
+int lfdm_attn_temporal_fused(const float* x, const float* gamma, const void* wq_packed, const void* wo_packed,
+                             const float* out_bias, const float* rot_cos, const float* rot_sin, const float* pos_bias,
+                             float* out_f32, void* out_sb, int64_t out_plane, int n_b, int frames, int pixels, int c,
+                             int heads, float eps, float* debug, void* stream);
+
 /* --- embeddings ---------------------------------------------------------------------------------------------- */
 /* y[r][n] = act_out( sum_k act_in(x[r][k]) W[n][k] + b[n] ), small-M GEMV-class (time_mlp :422-428, block mlp :217-220).
  * act_in/out: 0 none, 1 silu, 2 gelu(erf).                                                                    */
@@ -172,6 +185,12 @@ int lfdm_avgpool2_rows(const float* in, int n, int h, int w, int c, float* out_f
 /* final 1x1 heads (video_flow_diffusion.py:495,508,588): out[b][0:2|2][f][p] from two F32 row matrices            */
 int lfdm_unet_heads(const float* a, const float* wa, const float* ba, int na, const float* o, const float* wo,
                     const float* bo, int no, int c, int b, int f, int p, float* out, void* stream);
+
+/* classifier-free guidance form (Unet3D.forward_with_cond_scale, video_flow_diffusion.py:521-526): a / o hold a 2B batch,
+ * rows [0, B*f*p) evaluated with the condition and rows [B*f*p, 2*B*f*p) with the null condition;
+ * out[b] = null_logits + (logits - null_logits) * cond_scale, b < B.                                              */
+int lfdm_unet_heads_cfg(const float* a, const float* wa, const float* ba, int na, const float* o, const float* wo,
+                        const float* bo, int no, int c, int b, int f, int p, float cond_scale, float* out, void* stream);
 
 /* --- full-LFAE branch: dense motion / regions --------------------------------------- */
 /* AntiAliasInterpolation2d (LFAE/modules/util.py:256-264): depthwise ks x ks Gaussian (zero pad ka) + ::s subsample, NCHW */

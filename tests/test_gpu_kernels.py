@@ -284,6 +284,76 @@ def test_qkv_projection_with_fused_rotary_and_prescaled_attention():
     close(out, ref, "attention on pre-rotated q|k")
 
 
+def _temporal_block_reference(x_rows, gamma, wqkv, wout, out_bias, pos_bias, b, f, p, heads, eps=1e-5):
+    """float64 restatement of Residual(PreNorm(EinopsToAndFrom(Attention))) (reference :132-138,170-190,270-283,286-363)
+    on rows [(b*f + fi)*p + pi][c]; returns out rows and the intermediates the fused kernel can dump."""
+    from oracle import lfdm_oracle as O
+    hid = heads * 32
+    x = x_rows.double()
+    var = x.var(dim=1, unbiased=False, keepdim=True)
+    xn = (x - x.mean(1, keepdim=True)) / (var + eps).sqrt() * gamma.double()
+    qkv = (xn @ wqkv.double().t()).reshape(b, f, p, 3 * hid).permute(0, 2, 1, 3)       # (b, p, f, 3 hid)
+    q, k, v = [t.reshape(b, p, f, heads, 32).transpose(-2, -3) for t in qkv.chunk(3, -1)]   # (b, p, h, f, d)
+    freqs = O.rotary_freqs(32).double()
+    q = O.rotary_apply(q * 32 ** -0.5, freqs)
+    k = O.rotary_apply(k, freqs)
+    sim = torch.einsum("...hid,...hjd->...hij", q, k)
+    if pos_bias is not None:
+        sim = sim + pos_bias.double()
+    att = (sim - sim.amax(-1, keepdim=True)).softmax(-1)
+    o = torch.einsum("...hij,...hjd->...hid", att, v)                                   # (b, p, h, f, d)
+    rows = lambda t: t.permute(0, 3, 1, 2, 4).reshape(b * f * p, -1)                     # -> [(b, f, p)][h*d]
+    o_rows = rows(o)
+    out = o_rows @ wout.double().t() + x
+    if out_bias is not None:
+        out = out + out_bias.double()
+    att_rows = att.permute(0, 3, 1, 2, 4).reshape(b * f * p, heads * f)                  # row (b, fi, p): [h][j]
+    return out.float(), dict(q=rows(q).float(), k=rows(k).float(), v=rows(v).float(), att=att_rows.float(), o=o_rows.float())
+
+
+@pytest.mark.parametrize("b,p,heads,with_bias", [(2, 10, 8, False), (1, 7, 3, True), (3, 400, 8, False)])
+def test_temporal_attention_block_fused(b, p, heads, with_bias):
+    """lfdm_attn_temporal_fused (one tcgen05 kernel: LN -> qkv -> rotary -> softmax(QK^T + bias) V -> to_out -> + x) against
+    a float64 restatement, including the kernel's diagnostic dump of every intermediate; partial last tile, tiles that
+    straddle samples, several tiles per CTA (the third case has 400 tiles > 148 SMs)."""
+    from oracle import lfdm_oracle as O
+    from cvpr23_lfdm_b200.engine import ops
+    from cvpr23_lfdm_b200._lib import SB
+    g = torch.Generator().manual_seed(500 + p)
+    f, c, hid = 40, 64, heads * 32
+    m = b * f * p
+    x = torch.randn(m, c, generator=g) * 1.5 + 0.3
+    gamma = torch.randn(c, generator=g)
+    wqkv = torch.randn(3 * hid, c, generator=g) / 8
+    wout = torch.randn(c, hid, generator=g) / 16
+    ob = torch.randn(c, generator=g) if with_bias else None
+    pos = torch.randn(heads, f, f, generator=g)
+    ref, mid = _temporal_block_reference(x, gamma, wqkv, wout, ob, pos, b, f, p, heads)
+    ang = torch.outer(torch.arange(f).float(), O.rotary_freqs(32))
+    wq_img, wo_img = ops.pack_fused_attention(wqkv.to(dev()), wout.to(dev()), heads)
+    out, out_sb = torch.empty(m, c, device=dev()), SB(m, c, dev())
+    dbg = torch.zeros(m, 3 * hid + heads * f + hid, device=dev())
+    rc = ops.attn_temporal_fused(x.to(dev()), gamma.to(dev()), wq_img, wo_img, ob.to(dev()) if with_bias else None,
+                                 ang.cos().contiguous().to(dev()), ang.sin().contiguous().to(dev()), pos.to(dev()),
+                                 out, out_sb, b, f, p, heads, 1e-5, debug=dbg)
+    assert rc == 0
+    torch.cuda.synchronize()
+    d = dbg.cpu()
+    close(d[:, :hid], mid["q"], "fused block: rotated q")
+    close(d[:, hid:2 * hid], mid["k"], "fused block: rotated k")
+    close(d[:, 2 * hid:3 * hid], mid["v"], "fused block: v")
+    close(d[:, 3 * hid:3 * hid + heads * f], mid["att"], "fused block: softmax rows", atol=2e-5)
+    close(d[:, 3 * hid + heads * f:], mid["o"], "fused block: head outputs")
+    close(out, ref, "fused block: out f32")
+    close(out_sb.float(), ref, "fused block: out sb")
+    # without the diagnostic buffer (the production call) the result is the same
+    out2 = torch.empty(m, c, device=dev())
+    assert ops.attn_temporal_fused(x.to(dev()), gamma.to(dev()), wq_img, wo_img, ob.to(dev()) if with_bias else None,
+                                   ang.cos().contiguous().to(dev()), ang.sin().contiguous().to(dev()), pos.to(dev()),
+                                   out2, None, b, f, p, heads, 1e-5) == 0
+    assert torch.equal(out2, out)
+
+
 @pytest.mark.parametrize("f", [17, 24, 33, 39])
 def test_attn_temporal_ragged_lengths(f):
     """rotary + bias on frame counts that leave partial 16-row query tiles / odd bias rows (ldmatrix kernel, 17 <= L <= 40)"""

@@ -94,6 +94,38 @@ def cases():
         return run, 4.0 * B * p * heads * F * F * 32, m * 768 * 4 + m * 256 * 4, lambda: "mma.sync split-bf16, contiguous sequences"
     c["attn_temporal_32_contig"] = attn_tc
 
+    def tblock(fused, hw=32):
+        def mk():
+            p, heads, ch = hw * hw, 8, 64
+            m = B * F * p
+            x = torch.randn(m, ch, device=dev)
+            gamma = torch.randn(ch, device=dev)
+            wqkv, wout = torch.randn(768, ch, 1, 1, device=dev) / 8, torch.randn(ch, 256, 1, 1, device=dev) / 16
+            ang = torch.outer(torch.arange(F, device=dev).float(), 1.0 / (10000 ** (torch.arange(0, 32, 2, device=dev).float() / 32)))
+            cs, sn, bias = ang.cos().contiguous(), ang.sin().contiguous(), torch.randn(heads, F, F, device=dev)
+            out, out_sb = torch.empty(m, ch, device=dev), SB(m, ch, dev)
+            # algorithmic work of the block: LN + to_qkv + attention cores + to_out; bytes: x read, out written twice (F32 + SB)
+            flops = 2.0 * m * ch * 768 + 4.0 * B * p * heads * F * F * 32 + 2.0 * m * 256 * ch
+            byt = m * ch * 4 * 3
+            if fused:
+                wq_img, wo_img = ops.pack_fused_attention(wqkv, wout, heads)
+                run = lambda: ops.attn_temporal_fused(x, gamma, wq_img, wo_img, None, cs, sn, bias, out, out_sb, B, F, p, heads, 1e-5)
+                return run, flops, byt, lambda: "tcgen05 fused block (split-bf16 x3)"
+            lq, lo = ConvLayer(wqkv, None), ConvLayer(wout, None)
+            n_sb, qkv, o = SB(m, ch, dev), torch.empty(m, 768, device=dev), SB(m, 256, dev)
+
+            def run():
+                ops.layernorm(x, gamma, out_sb=n_sb)
+                lq([n_sb], B * F, hw, hw, out_f32=qkv)
+                ops.attn_softmax(qkv, o, None, B * p, F, heads, p, F * p, 1, p, cs, sn, bias)
+                lo([o], B * F, hw, hw, out_f32=out, out_sb=out_sb, residual=x)
+            return run, flops, byt, lambda: "4 kernels: layernorm + tcgen05 qkv + mma.sync core + tcgen05 out"
+        return mk
+    c["tblock_fused_32"] = tblock(True)
+    c["tblock_unfused_32"] = tblock(False)
+    c["tblock_fused_16"] = tblock(True, 16)
+    c["tblock_unfused_16"] = tblock(False, 16)
+
     def attn_l():
         p, heads = 1024, 8
         m = B * F * p
