@@ -71,9 +71,11 @@ def _declare(l):
         "lfdm_to_rows": [vp, i32, i32, i32, i32, i64, i64, i64, i32, vp, i64, vp, vp],
         "lfdm_from_rows": [vp, i32, i32, i32, i32, i32, vp, vp],
         "lfdm_im2col_small": [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp],
+        "lfdm_pad_replicate_rows": [vp, i64, vp, i64, i32, i32, i32, i32, vp],
         "lfdm_avgpool2_rows": [vp, i32, i32, i32, i32, vp, vp, i64, vp],
         "lfdm_unet_heads": [vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp],
         "lfdm_unet_heads_cfg": [vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp],
+        "lfdm_render_panels": [vp, vp, vp, vp, vp, C.POINTER(C.c_float), i32, i32, i32, i32, i32, f32, vp, vp, vp],
         "lfdm_split_bf16": [vp, vp, i64, i64, vp],
         "lfdm_antialias_down": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "lfdm_region_moments": [vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp],
@@ -92,8 +94,8 @@ EXPORTED = ["lfdm_conv", "lfdm_gn_stats", "lfdm_gn_apply", "lfdm_layernorm", "lf
             "lfdm_attn_linear", "lfdm_attn_temporal_fused",
             "lfdm_small_linear", "lfdm_sinusoidal", "lfdm_ss_combine", "lfdm_sampler_x0", "lfdm_sampler_quantile",
             "lfdm_sampler_update", "lfdm_warp_blend_rows", "lfdm_warp_blend_image", "lfdm_to_rows", "lfdm_from_rows",
-            "lfdm_im2col_small", "lfdm_avgpool2_rows", "lfdm_unet_heads", "lfdm_unet_heads_cfg", "lfdm_split_bf16", "lfdm_version",
-            "lfdm_antialias_down", "lfdm_region_moments", "lfdm_motion_prep", "lfdm_motion_finish", "lfdm_rows_mean"]
+            "lfdm_im2col_small", "lfdm_pad_replicate_rows", "lfdm_avgpool2_rows", "lfdm_unet_heads", "lfdm_unet_heads_cfg", "lfdm_split_bf16", "lfdm_version",
+            "lfdm_antialias_down", "lfdm_region_moments", "lfdm_motion_prep", "lfdm_motion_finish", "lfdm_rows_mean", "lfdm_render_panels"]
 
 launch_count = 0   # number of C-ABI calls issued (bench.py reports kernels launched per step from this)
 

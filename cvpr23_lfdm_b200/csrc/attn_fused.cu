@@ -7,19 +7,27 @@
 // ups.2, ups.3).  q|k|v, the scores and the per-head outputs never leave the SM: the four GEMM-shaped stages run on
 // tcgen05 with fp32 accumulators in TMEM, everything between them is done by two warp-groups straight out of TMEM.
 //
-// One tile = 3 pixel columns x 40 frames = 120 rows of the row matrix (padded to the 128-row UMMA tile).  Per tile:
-//   LN      : 256 threads, 16 lanes per row: x -> LayerNorm -> split-bf16 A operand (128x64, SW128 K-major) + fp32 copy
-//   per head h (weights streamed from L2 with cp.async.bulk into a 2-stage ring, pre-swizzled on the host):
-//     qkv   : D[128x96]  = Xn . W_h^T            (3 split-bf16 products x 4 K-steps, double-buffered TMEM)
-//     WG-A  : q*scale, rotary(q), rotary(k) from TMEM -> [hi|lo] operand rows in smem
-//     WG-B  : v from TMEM -> transposed "compact" B operand  V^T[(pixel, d)][j]
-//     QK    : S[128x128] = Q . K^T               (all 3 pixels at once; each row only uses its own 40-column block)
-//     WG-A  : +bias, softmax over the row's 40 columns, P -> compact A operand [128 x 48] (hi / lo planes)
-//     PV    : D[128x96]  = P . V^T^T             (column block 32*pixel(row) is the row's result)
-//     WG-B  : own 32 columns -> split-bf16 [hi|lo] operand rows
-//     out   : OUT[128x64] += O_h . Wout_h^T      (accumulated over heads in TMEM)
-//   epilogue: OUT + bias + x (kept in smem) -> F32 and split-bf16 rows, coalesced.
-// Synchronisation is mbarrier-only (tcgen05.commit for MMA completion, counted arrivals for the warp-groups).
+// One tile = 3 pixel columns x 40 frames = 120 rows of the row matrix (padded to the 128-row UMMA tile).  Roles:
+//   warp 0      MMA issuer (one elected thread), software-pipelined over the flat (tile, head) sequence:
+//                 QK(g+1) -> PV(g) -> qkv(g+2) -> out(g)         (scores double-buffered in TMEM: QK(g+1) runs while the
+//                 softmax of head g is still reading S(g); qkv runs ahead, also across tiles)
+//   warp 1      weight producer: per head one [W_hi|W_lo] slice of to_qkv (24 KiB) and of to_out (8 KiB), pre-swizzled on
+//               the host, cp.async.bulk from L2 into 2-stage rings
+//   warps 2-3   LayerNorm producers: the NEXT tile's x rows are loaded into registers while the current tile is being
+//               processed; as soon as the last qkv GEMM of the current tile has drained the operand buffer they normalise
+//               and write the split-bf16 A operand (128x64, SW128 K-major)
+//   warps 4-7   WG-A: q*scale, rotary(q), rotary(k) TMEM -> [hi|lo] operand rows
+//   warps 8-11  WG-B: v TMEM -> transposed compact B operand V^T[(pixel, d)][j]; PV result -> [hi|lo] operand rows of the
+//               output projection
+//   warps 12-15 WG-C: +bias, softmax over the row's 40 columns, P -> compact A operand [128 x 48] (hi / lo planes)
+//               (the three groups work on different heads at the same time: conversion(g+1) | softmax(g) | output(g-1))
+//   per head:   qkv  D[128x96]   = Xn . W_h^T          3 split-bf16 products x 4 K-steps, double-buffered TMEM
+//               QK   S[128x128]  = Q . K^T             all 3 pixels at once; a row only uses its own 40-column block
+//               PV   D[128x96]   = P . V^T^T           compact K = 48 positions; column block 32*pixel(row) is the result
+//               out  OUT[128x64] += O_h . Wout_h^T     accumulated over heads in TMEM
+//   epilogue:   (WG-B) OUT (+bias) + x -> F32 and split-bf16 rows, coalesced through the (then idle) P operand buffer.
+// Synchronisation: mbarriers (tcgen05.commit for MMA completion, one elected arrival per warp) + one named barrier
+// (epilogue).  Shared memory is addressed with explicit st.shared / ld.shared on 32-bit addresses.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -28,32 +36,32 @@ namespace {
 constexpr int FL = 40;       // frames (sequence length)
 constexpr int FG = 3;        // pixel columns per tile
 constexpr int FC = 64;       // channels
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 512;
 
 constexpr int OFF_XN = 0;            // 2 planes x 16 KiB : LayerNorm output, A operand of the qkv GEMM
 constexpr int OFF_Q = 32768;         // 16 KiB : rows [q_hi(32) | q_lo(32)]
 constexpr int OFF_K = 49152;         // 16 KiB : rows [k_hi | k_lo]
 constexpr int OFF_VT = 65536;        // 2 planes x 12 KiB : V^T, 96 rows (pixel, d) x 64 positions (48 used)
 constexpr int VT_PLANE = 12288;
-constexpr int OFF_P = 90112;         // 2 planes x 16 KiB : P rows x 64 positions (48 used); hi plane doubles as the O tile
-constexpr int OFF_WQ = 122880;       // 2 stages x 24 KiB : [W_hi (96 x 64) | W_lo (96 x 64)] of one head
+constexpr int OFF_P = 90112;         // 2 planes x 16 KiB : P rows x 64 positions (48 used, 40..47 zero); fp32 staging tile of the epilogue
+constexpr int OFF_O = 122880;        // 16 KiB : rows [o_hi(32) | o_lo(32)]
+constexpr int OFF_WQ = 139264;       // 2 stages x 24 KiB : [W_hi (96 x 64) | W_lo (96 x 64)] of one head
 constexpr int WQ_STAGE = 24576;
-constexpr int OFF_WO = 172032;       // 2 stages x 8 KiB : 64 rows [w_hi(32) | w_lo(32)] of one head
+constexpr int OFF_WO = 188416;       // 2 stages x 8 KiB : 64 rows [w_hi(32) | w_lo(32)] of one head
 constexpr int WO_STAGE = 8192;
-constexpr int OFF_XR = 188416;       // 32 KiB : fp32 copy of the x tile (residual + coalescing stage of the output)
-constexpr int OFF_BAR = 221184;
-constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+constexpr int OFF_BAR = 204800;      // mbarriers, TMEM pointer
+constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;
 
 // TMEM column map (512 columns allocated)
-constexpr uint32_t T_QKV = 0;        // 2 x 96
-constexpr uint32_t T_S = 192;        // 128
-constexpr uint32_t T_PVD = 320;      // 96
-constexpr uint32_t T_OUT = 416;      // 64
+constexpr uint32_t T_QKV = 0;        // 96
+constexpr uint32_t T_S = 96;         // 2 x 128 (double-buffered scores)
+constexpr uint32_t T_PVD = 352;      // 96
+constexpr uint32_t T_OUT = 448;      // 64
 
 enum {
-    B_XN_FULL = 0, B_WQ_FULL = 1, B_WQ_EMPTY = 3, B_WO_FULL = 5, B_WO_EMPTY = 7, B_QKV_FULL = 9, B_QKV_EMPTY = 11,
-    B_QK_READY = 13, B_S_FULL = 14, B_P_READY = 15, B_VT_READY = 16, B_PVD_FULL = 17, B_O_READY = 18, B_OUT_FULL = 19,
-    B_OUT_EMPTY = 20, B_COUNT = 21
+    B_XN_FULL = 0, B_XN_EMPTY = 1, B_WQ_FULL = 2, B_WQ_EMPTY = 4, B_WO_FULL = 6, B_WO_EMPTY = 8, B_QKV_FULL = 10,
+    B_QKV_EMPTY = 11, B_QK_READY = 12, B_S_FULL = 13 /* 2 */, B_P_READY = 16, B_VT_READY = 17, B_PVD_FULL = 18, B_O_READY = 19,
+    B_OUT_FULL = 20, B_OUT_EMPTY = 21, B_STG_FREE = 22
 };
 
 struct FusedArgs {
@@ -96,6 +104,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
     const float2 hf = __bfloat1622float2(h);
@@ -103,29 +116,124 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+__device__ __forceinline__ uint64_t* bar_at(uint8_t* smem, int i) { return reinterpret_cast<uint64_t*>(smem + OFF_BAR) + i; }
 // byte offset of 16-byte chunk `c` of row `r` in a SW128 K-major tile (rows of 128 B, 8-row groups of 1024 B)
 __device__ __forceinline__ uint32_t sw_off(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
 
-// 32 fp32 values of one row -> [hi(32) | lo(32)] operand row (chunks 0-3 hi, 4-7 lo)
-__device__ __forceinline__ void store_hilo_row(uint8_t* tile, int r, const float (&v)[32]) {
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint16_t a) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(a) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// 16 fp32 values (dims 16*half .. 16*half+15) of one row -> [hi(32) | lo(32)] operand row (chunks 0-3 hi, 4-7 lo)
+__device__ __forceinline__ void store_hilo_half(uint32_t tile, int r, int half, const float (&v)[16]) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint4 h, l;
-        split2(v[8 * c], v[8 * c + 1], h.x, l.x);
-        split2(v[8 * c + 2], v[8 * c + 3], h.y, l.y);
-        split2(v[8 * c + 4], v[8 * c + 5], h.z, l.z);
-        split2(v[8 * c + 6], v[8 * c + 7], h.w, l.w);
-        *reinterpret_cast<uint4*>(tile + sw_off(r, c)) = h;
-        *reinterpret_cast<uint4*>(tile + sw_off(r, c + 4)) = l;
+    for (int c = 0; c < 2; ++c) {
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split2(v[8 * c], v[8 * c + 1], h0, l0);
+        split2(v[8 * c + 2], v[8 * c + 3], h1, l1);
+        split2(v[8 * c + 4], v[8 * c + 5], h2, l2);
+        split2(v[8 * c + 6], v[8 * c + 7], h3, l3);
+        sts128(tile + sw_off(r, 2 * half + c), h0, h1, h2, h3);
+        sts128(tile + sw_off(r, 2 * half + c + 4), l0, l1, l2, l3);
+    }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// one arrival per warp: all lanes have finished their part (and fenced it) before lane 0 signals
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(bar);
+}
+
+// softmax over the 40 columns of row r (TMEM block at column 40*pixel) -> normalised probabilities as split-bf16 chunks 0..4
+template <bool DBG>
+__device__ __forceinline__ void softmax_row(const FusedArgs& a, uint8_t* smem, uint32_t sb, uint32_t t_s, int r, int px, int pxlo,
+                                            int pxhi, bool straddle, int fr, int h, uint32_t g, uint32_t stg_it, int64_t my_grow,
+                                            int dbg_ld, int hid) {
+    constexpr float L2E = 1.4426950408889634f;
+    float sv[FL];
+    {
+        const bool use_hi = straddle && px != pxlo;
+#pragma unroll
+        for (int c = 0; c < FL / 8; ++c) {       // 8 columns at a time keeps the live register set small
+            uint32_t u0[8], u1[8];
+            tmem_ld8(t_s + (uint32_t)(FL * pxlo + 8 * c), u0);
+            if (straddle) tmem_ld8(t_s + (uint32_t)(FL * pxhi + 8 * c), u1);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sv[8 * c + j] = __uint_as_float(use_hi ? u1[j] : u0[j]);
+        }
+    }
+    if (a.pos_bias) {      // T5 relative-position bias row (h, frame): L1 / L2 resident
+        const float4* bp = reinterpret_cast<const float4*>(a.pos_bias + ((int64_t)h * FL + fr) * FL);
+#pragma unroll
+        for (int i = 0; i < FL / 4; ++i) {
+            const float4 t4 = __ldg(bp + i);
+            sv[4 * i] += t4.x; sv[4 * i + 1] += t4.y; sv[4 * i + 2] += t4.z; sv[4 * i + 3] += t4.w;
+        }
+    }
+    float m0 = fmaxf(sv[0], sv[1]), m1 = fmaxf(sv[2], sv[3]), m2 = fmaxf(sv[4], sv[5]), m3 = fmaxf(sv[6], sv[7]);
+#pragma unroll
+    for (int j = 8; j < FL; j += 4) {
+        m0 = fmaxf(m0, sv[j]); m1 = fmaxf(m1, sv[j + 1]); m2 = fmaxf(m2, sv[j + 2]); m3 = fmaxf(m3, sv[j + 3]);
+    }
+    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    const float nb = -mx * L2E;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < FL; j += 4) {
+        sv[j] = ex2(fmaf(sv[j], L2E, nb)); sv[j + 1] = ex2(fmaf(sv[j + 1], L2E, nb));
+        sv[j + 2] = ex2(fmaf(sv[j + 2], L2E, nb)); sv[j + 3] = ex2(fmaf(sv[j + 3], L2E, nb));
+        s0 += sv[j]; s1 += sv[j + 1]; s2 += sv[j + 2]; s3 += sv[j + 3];
+    }
+    const float inv = 1.f / ((s0 + s1) + (s2 + s3));
+#pragma unroll
+    for (int j = 0; j < FL; ++j) sv[j] *= inv;
+    if (DBG) {
+        if (a.dbg && my_grow >= 0) {
+#pragma unroll
+            for (int j = 0; j < FL; ++j) a.dbg[my_grow * dbg_ld + 3 * hid + h * FL + j] = sv[j];
+        }
+    }
+    // P is single-buffered: PV of the previous head must have read it (its scores were computed ahead of it), and on the first
+    // head of a tile the epilogue of the previous tile must have released the buffer it uses as its staging tile
+    if (g > 0) ptx::mbar_wait(bar_at(smem, B_PVD_FULL), (g - 1) & 1);
+    if (stg_it > 0) ptx::mbar_wait(bar_at(smem, B_STG_FREE), (stg_it - 1) & 1);
+#pragma unroll
+    for (int c = 0; c < FL / 8; ++c) {
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split2(sv[8 * c], sv[8 * c + 1], h0, l0);
+        split2(sv[8 * c + 2], sv[8 * c + 3], h1, l1);
+        split2(sv[8 * c + 4], sv[8 * c + 5], h2, l2);
+        split2(sv[8 * c + 6], sv[8 * c + 7], h3, l3);
+        sts128(sb + OFF_P + sw_off(r, c), h0, h1, h2, h3);
+        sts128(sb + OFF_P + 16384 + sw_off(r, c), l0, l1, l2, l3);
     }
 }
 
-__device__ __forceinline__ uint64_t* bar_at(uint8_t* smem, int i) { return reinterpret_cast<uint64_t*>(smem + OFF_BAR) + i; }
-
+template <bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const __grid_constant__ FusedArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 256);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 512);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const int heads = a.heads;
@@ -133,31 +241,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
 
     pdl_trigger();
     if (warp == 1 && ptx::elect_one()) {
-        ptx::mbar_init(bar_at(smem, B_XN_FULL), 256);
+        ptx::mbar_init(bar_at(smem, B_XN_FULL), 2);
+        ptx::mbar_init(bar_at(smem, B_XN_EMPTY), 1);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(bar_at(smem, B_WQ_FULL + i), 1);
             ptx::mbar_init(bar_at(smem, B_WQ_EMPTY + i), 1);
             ptx::mbar_init(bar_at(smem, B_WO_FULL + i), 1);
             ptx::mbar_init(bar_at(smem, B_WO_EMPTY + i), 1);
-            ptx::mbar_init(bar_at(smem, B_QKV_FULL + i), 1);
-            ptx::mbar_init(bar_at(smem, B_QKV_EMPTY + i), 256);
+            ptx::mbar_init(bar_at(smem, B_S_FULL + i), 1);
         }
-        ptx::mbar_init(bar_at(smem, B_QK_READY), 128);
-        ptx::mbar_init(bar_at(smem, B_S_FULL), 1);
-        ptx::mbar_init(bar_at(smem, B_P_READY), 128);
-        ptx::mbar_init(bar_at(smem, B_VT_READY), 128);
+        ptx::mbar_init(bar_at(smem, B_QKV_FULL), 1);
+        ptx::mbar_init(bar_at(smem, B_QKV_EMPTY), 8);
+        ptx::mbar_init(bar_at(smem, B_QK_READY), 4);
+        ptx::mbar_init(bar_at(smem, B_STG_FREE), 4);
+        ptx::mbar_init(bar_at(smem, B_P_READY), 4);
+        ptx::mbar_init(bar_at(smem, B_VT_READY), 4);
         ptx::mbar_init(bar_at(smem, B_PVD_FULL), 1);
-        ptx::mbar_init(bar_at(smem, B_O_READY), 128);
+        ptx::mbar_init(bar_at(smem, B_O_READY), 4);
         ptx::mbar_init(bar_at(smem, B_OUT_FULL), 1);
-        ptx::mbar_init(bar_at(smem, B_OUT_EMPTY), 256);
+        ptx::mbar_init(bar_at(smem, B_OUT_EMPTY), 4);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
         ptx::tmem_alloc(tmem_ptr, 512);
         ptx::tmem_relinquish();
     }
-    // V^T pad positions (40..47 of every row) are never written afterwards: zero the operand once
-    for (int i = threadIdx.x; i < (2 * VT_PLANE) / 16; i += NTHREADS)
+    // V^T pad positions (40..47 of every row) and P positions 40..63 are never written afterwards: zero both operands once
+    for (int i = threadIdx.x; i < (OFF_O - OFF_VT) / 16; i += NTHREADS)
         reinterpret_cast<uint4*>(smem + OFF_VT)[i] = make_uint4(0u, 0u, 0u, 0u);
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
@@ -167,22 +277,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
     pdl_wait();
 
     const int n_tiles = a.n_tiles;
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t NG = (uint32_t)(my_tiles * heads);        // flat (tile, head) sequence of this CTA
 
     if (warp == 1) {
-        // ===================== weight producer: one head's W_qkv / W_out slices per ring stage =====================
+        // ===================== weight producer =====================
         if (ptx::elect_one()) {
-            uint32_t g = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int h = 0; h < heads; ++h, ++g) {
-                    const int s = g & 1;
-                    const uint32_t par = ((g >> 1) & 1) ^ 1;
-                    ptx::mbar_wait(bar_at(smem, B_WQ_EMPTY + s), par);
-                    ptx::mbar_arrive_expect_tx(bar_at(smem, B_WQ_FULL + s), WQ_STAGE);
-                    bulk_copy_g2s(smem + OFF_WQ + s * WQ_STAGE, a.wq + (size_t)h * WQ_STAGE, WQ_STAGE, bar_at(smem, B_WQ_FULL + s));
-                    ptx::mbar_wait(bar_at(smem, B_WO_EMPTY + s), par);
-                    ptx::mbar_arrive_expect_tx(bar_at(smem, B_WO_FULL + s), WO_STAGE);
-                    bulk_copy_g2s(smem + OFF_WO + s * WO_STAGE, a.wo + (size_t)h * WO_STAGE, WO_STAGE, bar_at(smem, B_WO_FULL + s));
-                }
+            int h = 0;
+            for (uint32_t g = 0; g < NG; ++g) {
+                const int s = g & 1;
+                const uint32_t par = ((g >> 1) & 1) ^ 1;
+                ptx::mbar_wait(bar_at(smem, B_WQ_EMPTY + s), par);
+                ptx::mbar_arrive_expect_tx(bar_at(smem, B_WQ_FULL + s), WQ_STAGE);
+                bulk_copy_g2s(smem + OFF_WQ + s * WQ_STAGE, a.wq + (size_t)h * WQ_STAGE, WQ_STAGE, bar_at(smem, B_WQ_FULL + s));
+                ptx::mbar_wait(bar_at(smem, B_WO_EMPTY + s), par);
+                ptx::mbar_arrive_expect_tx(bar_at(smem, B_WO_FULL + s), WO_STAGE);
+                bulk_copy_g2s(smem + OFF_WO + s * WO_STAGE, a.wo + (size_t)h * WO_STAGE, WO_STAGE, bar_at(smem, B_WO_FULL + s));
+                if (++h == heads) h = 0;
             }
         }
     } else if (warp == 0) {
@@ -194,18 +305,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
             const uint64_t d_k = ptx::make_sw128_kmajor_desc(sb + OFF_K);
             const uint64_t d_vt = ptx::make_sw128_kmajor_desc(sb + OFF_VT);
             const uint64_t d_p = ptx::make_sw128_kmajor_desc(sb + OFF_P);
+            const uint64_t d_o = ptx::make_sw128_kmajor_desc(sb + OFF_O);
             const uint64_t d_wq = ptx::make_sw128_kmajor_desc(sb + OFF_WQ);
             const uint64_t d_wo = ptx::make_sw128_kmajor_desc(sb + OFF_WO);
             constexpr uint32_t ID96 = ptx::make_idesc_bf16(128, 96);
             constexpr uint32_t ID128 = ptx::make_idesc_bf16(128, 128);
             constexpr uint32_t ID64 = ptx::make_idesc_bf16(128, 64);
+            // flat index g -> (tile iteration, head) without divisions: the three cursors advance monotonically
+            uint32_t q_it = 0; int q_h = 0;                  // cursor of issue_qkv
             auto issue_qkv = [&](uint32_t gq) {
-                const int s = gq & 1;
-                const uint32_t par = (gq >> 1) & 1;
-                ptx::mbar_wait(bar_at(smem, B_WQ_FULL + s), par);
-                ptx::mbar_wait(bar_at(smem, B_QKV_EMPTY + s), par ^ 1);
+                const int s = gq & 1;                         // weight ring stage
+                if (q_h == 0) ptx::mbar_wait(bar_at(smem, B_XN_FULL), q_it & 1);      // this tile's LayerNorm operand is in place
+                ptx::mbar_wait(bar_at(smem, B_WQ_FULL + s), (gq >> 1) & 1);
+                ptx::mbar_wait(bar_at(smem, B_QKV_EMPTY), (gq & 1) ^ 1);             // q | k | v of head gq-1 have been read
                 ptx::tc_fence_after();
-                const uint32_t td = tmem_base + T_QKV + 96u * (uint32_t)s;
+                const uint32_t td = tmem_base + T_QKV;
                 const uint64_t w_hi = d_wq + (uint64_t)((s * WQ_STAGE) >> 4), w_lo = w_hi + (uint64_t)(12288 >> 4);
                 const uint64_t x_hi = d_xn, x_lo = d_xn + (uint64_t)(16384 >> 4);
 #pragma unroll
@@ -216,73 +330,129 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                     ptx::umma_bf16(td, x_hi + o, w_hi + o, ID96, 1u);
                 }
                 ptx::umma_commit(bar_at(smem, B_WQ_EMPTY + s));
-                ptx::umma_commit(bar_at(smem, B_QKV_FULL + s));
-            };
-            uint32_t g = 0, it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                ptx::mbar_wait(bar_at(smem, B_XN_FULL), it & 1);
-                ptx::tc_fence_after();
-                issue_qkv(g);
-                for (int h = 0; h < heads; ++h) {
-                    const uint32_t gh = g + (uint32_t)h;
-                    if (h + 1 < heads) issue_qkv(gh + 1);
-                    // ---- S = Q K^T : rows [hi | lo]: K-steps 0,1 = hi dims, 2,3 = lo dims
-                    ptx::mbar_wait(bar_at(smem, B_QK_READY), gh & 1);
-                    ptx::tc_fence_after();
-                    {
-                        const uint32_t td = tmem_base + T_S;
-                        ptx::umma_bf16(td, d_q + 4, d_k + 0, ID128, 0u);      // q_lo . k_hi
-                        ptx::umma_bf16(td, d_q + 6, d_k + 2, ID128, 1u);
-                        ptx::umma_bf16(td, d_q + 0, d_k + 4, ID128, 1u);      // q_hi . k_lo
-                        ptx::umma_bf16(td, d_q + 2, d_k + 6, ID128, 1u);
-                        ptx::umma_bf16(td, d_q + 0, d_k + 0, ID128, 1u);      // q_hi . k_hi
-                        ptx::umma_bf16(td, d_q + 2, d_k + 2, ID128, 1u);
-                    }
-                    ptx::umma_commit(bar_at(smem, B_S_FULL));
-                    // ---- D = P V : compact K = 48 positions; D column block 32*pixel
-                    ptx::mbar_wait(bar_at(smem, B_P_READY), gh & 1);
-                    ptx::mbar_wait(bar_at(smem, B_VT_READY), gh & 1);
-                    ptx::tc_fence_after();
-                    {
-                        const uint32_t td = tmem_base + T_PVD;
-                        const uint64_t p_hi = d_p, p_lo = d_p + (uint64_t)(16384 >> 4);
-                        const uint64_t v_hi = d_vt, v_lo = d_vt + (uint64_t)(VT_PLANE >> 4);
-#pragma unroll
-                        for (int ks = 0; ks < 3; ++ks) {
-                            const uint64_t o = (uint64_t)(ks * 2);
-                            ptx::umma_bf16(td, p_lo + o, v_hi + o, ID96, ks > 0 ? 1u : 0u);
-                            ptx::umma_bf16(td, p_hi + o, v_lo + o, ID96, 1u);
-                            ptx::umma_bf16(td, p_hi + o, v_hi + o, ID96, 1u);
-                        }
-                    }
-                    ptx::umma_commit(bar_at(smem, B_PVD_FULL));
-                    // ---- OUT += O_h Wout_h^T
-                    const int so = gh & 1;
-                    ptx::mbar_wait(bar_at(smem, B_O_READY), gh & 1);
-                    ptx::mbar_wait(bar_at(smem, B_WO_FULL + so), (gh >> 1) & 1);
-                    if (h == 0) ptx::mbar_wait(bar_at(smem, B_OUT_EMPTY), (it & 1) ^ 1);
-                    ptx::tc_fence_after();
-                    {
-                        const uint32_t td = tmem_base + T_OUT;
-                        const uint64_t w = d_wo + (uint64_t)((so * WO_STAGE) >> 4);
-                        const uint64_t o_t = d_p;      // O tile lives in the P hi plane
-                        ptx::umma_bf16(td, o_t + 4, w + 0, ID64, h > 0 ? 1u : 0u);   // o_lo . w_hi
-                        ptx::umma_bf16(td, o_t + 6, w + 2, ID64, 1u);
-                        ptx::umma_bf16(td, o_t + 0, w + 4, ID64, 1u);               // o_hi . w_lo
-                        ptx::umma_bf16(td, o_t + 2, w + 6, ID64, 1u);
-                        ptx::umma_bf16(td, o_t + 0, w + 0, ID64, 1u);               // o_hi . w_hi
-                        ptx::umma_bf16(td, o_t + 2, w + 2, ID64, 1u);
-                    }
-                    ptx::umma_commit(bar_at(smem, B_WO_EMPTY + so));
-                    if (h == heads - 1) ptx::umma_commit(bar_at(smem, B_OUT_FULL));
+                ptx::umma_commit(bar_at(smem, B_QKV_FULL));
+                if (++q_h == heads) {                       // last qkv GEMM of the tile: the operand buffer may be refilled
+                    ptx::umma_commit(bar_at(smem, B_XN_EMPTY));
+                    q_h = 0; ++q_it;
                 }
-                g += (uint32_t)heads;
+            };
+            auto issue_qk = [&](uint32_t gk) {
+                // S[gk & 1] = Q K^T : rows [hi | lo]: K-steps 0,1 = hi dims, 2,3 = lo dims.  The buffer was last read by the
+                // softmax of head gk-2, whose P_READY this thread has already waited for.
+                ptx::mbar_wait(bar_at(smem, B_QK_READY), gk & 1);
+                ptx::tc_fence_after();
+                const uint32_t td = tmem_base + T_S + 128u * (gk & 1u);
+                ptx::umma_bf16(td, d_q + 4, d_k + 0, ID128, 0u);      // q_lo . k_hi
+                ptx::umma_bf16(td, d_q + 6, d_k + 2, ID128, 1u);
+                ptx::umma_bf16(td, d_q + 0, d_k + 4, ID128, 1u);      // q_hi . k_lo
+                ptx::umma_bf16(td, d_q + 2, d_k + 6, ID128, 1u);
+                ptx::umma_bf16(td, d_q + 0, d_k + 0, ID128, 1u);      // q_hi . k_hi
+                ptx::umma_bf16(td, d_q + 2, d_k + 2, ID128, 1u);
+                ptx::umma_commit(bar_at(smem, B_S_FULL + (gk & 1)));
+            };
+            if (NG > 0) {
+                issue_qkv(0);
+                issue_qk(0);
+                if (NG > 1) issue_qkv(1);
+            }
+            uint32_t it = 0; int h = 0;
+            for (uint32_t g = 0; g < NG; ++g) {
+                if (g + 1 < NG) issue_qk(g + 1);             // next head's scores while the softmax of head g is running
+                // ---- D = P V : compact K = 48 positions; D column block 32*pixel
+                ptx::mbar_wait(bar_at(smem, B_P_READY), g & 1);
+                ptx::mbar_wait(bar_at(smem, B_VT_READY), g & 1);
+                ptx::tc_fence_after();
+                {
+                    const uint32_t td = tmem_base + T_PVD;
+                    const uint64_t p_hi = d_p, p_lo = d_p + (uint64_t)(16384 >> 4);
+                    const uint64_t v_hi = d_vt, v_lo = d_vt + (uint64_t)(VT_PLANE >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) {
+                        const uint64_t o = (uint64_t)(ks * 2);
+                        ptx::umma_bf16(td, p_lo + o, v_hi + o, ID96, ks > 0 ? 1u : 0u);
+                        ptx::umma_bf16(td, p_hi + o, v_lo + o, ID96, 1u);
+                        ptx::umma_bf16(td, p_hi + o, v_hi + o, ID96, 1u);
+                    }
+                }
+                ptx::umma_commit(bar_at(smem, B_PVD_FULL));
+                const bool last_head = (h == heads - 1);
+                // qkv(g+2) needs v of head g+1 scattered by WG-B; on a tile's last head WG-B first runs the epilogue, which waits
+                // for OUT_FULL: there the output projection goes first
+                if (!last_head && g + 2 < NG) issue_qkv(g + 2);
+                // ---- OUT += O_h Wout_h^T
+                const int so = g & 1;
+                ptx::mbar_wait(bar_at(smem, B_O_READY), g & 1);
+                ptx::mbar_wait(bar_at(smem, B_WO_FULL + so), (g >> 1) & 1);
+                if (h == 0) ptx::mbar_wait(bar_at(smem, B_OUT_EMPTY), (it & 1) ^ 1);
+                ptx::tc_fence_after();
+                {
+                    const uint32_t td = tmem_base + T_OUT;
+                    const uint64_t w = d_wo + (uint64_t)((so * WO_STAGE) >> 4);
+                    ptx::umma_bf16(td, d_o + 4, w + 0, ID64, h > 0 ? 1u : 0u);   // o_lo . w_hi
+                    ptx::umma_bf16(td, d_o + 6, w + 2, ID64, 1u);
+                    ptx::umma_bf16(td, d_o + 0, w + 4, ID64, 1u);               // o_hi . w_lo
+                    ptx::umma_bf16(td, d_o + 2, w + 6, ID64, 1u);
+                    ptx::umma_bf16(td, d_o + 0, w + 0, ID64, 1u);               // o_hi . w_hi
+                    ptx::umma_bf16(td, d_o + 2, w + 2, ID64, 1u);
+                }
+                ptx::umma_commit(bar_at(smem, B_WO_EMPTY + so));
+                if (last_head) {
+                    ptx::umma_commit(bar_at(smem, B_OUT_FULL));
+                    if (g + 2 < NG) issue_qkv(g + 2);
+                    h = 0; ++it;
+                } else {
+                    ++h;
+                }
             }
         }
-    } else if (warp >= 4) {
-        // ===================== two compute warp-groups: A = warps 4-7, B = warps 8-11 =====================
-        const int tc = (int)threadIdx.x - 128;          // 0..255
-        const int wg = tc >> 7;                          // 0: A, 1: B
+    } else if (warp == 2 || warp == 3) {
+        // ===================== LayerNorm producers: x rows of the next tile -> registers -> XN =====================
+        const int t64 = (int)threadIdx.x - 64;          // 0..63
+        const int l16 = t64 & 15, rg = t64 >> 4;        // 16 lanes per row, 4 rows per pass, 32 passes
+        const float4 gam = *reinterpret_cast<const float4*>(a.gamma + l16 * 4);
+        const uint32_t sb_ln = ptx::smem_u32(smem) + OFF_XN;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float4 v[16];
+#pragma unroll
+                for (int p = 0; p < 16; ++p) {
+                    const int row = (half * 16 + p) * 4 + rg;
+                    const int tpx = row / FL, tf = row - tpx * FL;
+                    const int pc = tile * FG + tpx;
+                    const bool ok = row < FG * FL && pc < a.n_pc;
+                    const int64_t grow = ok ? ((int64_t)(pc / a.pix) * FL + tf) * a.pix + (pc % a.pix) : 0;
+                    v[p] = ok ? *reinterpret_cast<const float4*>(a.x + grow * FC + l16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (half == 0) ptx::mbar_wait(bar_at(smem, B_XN_EMPTY), (it & 1) ^ 1);     // previous tile's qkv GEMMs are done with XN
+#pragma unroll
+                for (int p = 0; p < 16; ++p) {
+                    const int row = (half * 16 + p) * 4 + rg;
+                    float s = (v[p].x + v[p].y) + (v[p].z + v[p].w);
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    const float mean = s / (float)FC;
+                    const float d0 = v[p].x - mean, d1 = v[p].y - mean, d2 = v[p].z - mean, d3 = v[p].w - mean;
+                    float sq = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    const float rstd = 1.f / sqrtf(sq / (float)FC + a.eps);
+                    uint2 hv, lv;
+                    split2(d0 * rstd * gam.x, d1 * rstd * gam.y, hv.x, lv.x);
+                    split2(d2 * rstd * gam.z, d3 * rstd * gam.w, hv.y, lv.y);
+                    const uint32_t off = sb_ln + sw_off(row, l16 >> 1) + ((l16 & 1) << 3);
+                    sts64(off, hv.x, hv.y);
+                    sts64(off + 16384, lv.x, lv.y);
+                }
+            }
+            ptx::fence_proxy_async();
+            warp_arrive(bar_at(smem, B_XN_FULL), lane);
+        }
+    } else {
+        // ===================== three compute warp-groups: A = warps 4-7, B = warps 8-11, C = warps 12-15 =====================
+        const int tc = (int)threadIdx.x - 128;          // 0..383
+        const int wg = tc >> 7;                          // 0: A (q, k), 1: B (v, O, epilogue), 2: C (softmax)
         const int q = warp & 3;                          // TMEM lane quarter
         const int r = q * 32 + lane;                     // tile row of this thread
         const int rpx = r / FL;                          // 0..3 (3 = pad rows)
@@ -294,12 +464,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
         const int pxhi = pxhi_raw < FG ? pxhi_raw : FG - 1;
         const bool straddle = pxhi != pxlo;              // warp-uniform
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* xr = reinterpret_cast<float*>(smem + OFF_XR);
+        const uint32_t sb = ptx::smem_u32(smem);
         const int dbg_ld = 3 * hid + heads * FL + hid;
 
-        // rotary table row of this thread's frame (WG-A only uses it)
-        float rc[16], rs[16];
         if (wg == 0) {
+            // ---------- WG-A: q*scale, rotary(q), rotary(k) -> operand rows, head after head across tiles ----------
+            float rc[16], rs[16];                        // rotary table row of this thread's frame
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
                 const float4 c4 = *reinterpret_cast<const float4*>(a.rot_cos + fr * 16 + i);
@@ -307,247 +477,197 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                 rc[i] = c4.x; rc[i + 1] = c4.y; rc[i + 2] = c4.z; rc[i + 3] = c4.w;
                 rs[i] = s4.x; rs[i + 1] = s4.y; rs[i + 2] = s4.z; rs[i + 3] = s4.w;
             }
-        }
-        const int l16 = tc & 15, rg = tc >> 4;           // LayerNorm / store mapping: 16 lanes per row, 16 rows per pass
-        const float4 gam = *reinterpret_cast<const float4*>(a.gamma + l16 * 4);
-        float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.out_bias) ob = *reinterpret_cast<const float4*>(a.out_bias + l16 * 4);
-
-        uint32_t g = 0, it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            // ---------------- LayerNorm of the x tile -> XN (split-bf16 operand) + XR (fp32) ----------------
-            {
-                float4 v[8];
-                int64_t grow[8];
-#pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const int row = p * 16 + rg;
-                    const int tpx = row / FL, tf = row - tpx * FL;
-                    const int pc = tile * FG + tpx;
-                    const bool ok = row < FG * FL && pc < a.n_pc;
-                    grow[p] = ok ? ((int64_t)(pc / a.pix) * FL + tf) * a.pix + (pc % a.pix) : -1;
-                    v[p] = ok ? *reinterpret_cast<const float4*>(a.x + grow[p] * FC + l16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int64_t my_grow = -1;
+                if (DBG) {
+                    const int pc = tile * FG + rpx;
+                    if (row_real && pc < a.n_pc) my_grow = ((int64_t)(pc / a.pix) * FL + fr) * a.pix + (pc % a.pix);
                 }
-#pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const int row = p * 16 + rg;
-                    float s = (v[p].x + v[p].y) + (v[p].z + v[p].w);
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    const float mean = s / (float)FC;
-                    const float d0 = v[p].x - mean, d1 = v[p].y - mean, d2 = v[p].z - mean, d3 = v[p].w - mean;
-                    float sq = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                    const float rstd = 1.f / sqrtf(sq / (float)FC + a.eps);
-                    const float n0 = d0 * rstd * gam.x, n1 = d1 * rstd * gam.y, n2 = d2 * rstd * gam.z, n3 = d3 * rstd * gam.w;
-                    uint2 hv, lv;
-                    split2(n0, n1, hv.x, lv.x);
-                    split2(n2, n3, hv.y, lv.y);
-                    const uint32_t off = sw_off(row, l16 >> 1) + ((l16 & 1) << 3);
-                    *reinterpret_cast<uint2*>(smem + OFF_XN + off) = hv;
-                    *reinterpret_cast<uint2*>(smem + OFF_XN + 16384 + off) = lv;
-                    reinterpret_cast<float4*>(xr)[row * 16 + (l16 ^ (row & 7))] = v[p];
-                }
-                ptx::fence_proxy_async();
-                ptx::mbar_arrive(bar_at(smem, B_XN_FULL));
-            }
-            // global row of this thread's tile row (diagnostics only)
-            int64_t my_grow = -1;
-            {
-                const int pc = tile * FG + rpx;
-                if (row_real && pc < a.n_pc) my_grow = ((int64_t)(pc / a.pix) * FL + fr) * a.pix + (pc % a.pix);
-            }
-
-            for (int h = 0; h < heads; ++h) {
-                const uint32_t gh = g + (uint32_t)h;
-                const int b = gh & 1;
-                const uint32_t t_qkv = lane_base + T_QKV + 96u * (uint32_t)b;
-                if (wg == 0) {
-                    // ---------- WG-A: q, k -> operand rows ----------
-                    ptx::mbar_wait(bar_at(smem, B_QKV_FULL + b), (gh >> 1) & 1);
+                for (int h = 0; h < heads; ++h, ++g) {
+                    const uint32_t t_qkv = lane_base + T_QKV;
+                    ptx::mbar_wait(bar_at(smem, B_QKV_FULL), g & 1);
+                    if (g > 0) ptx::mbar_wait(bar_at(smem, B_S_FULL + ((g - 1) & 1)), ((g - 1) >> 1) & 1);   // QK(g-1) is done with Q / K
                     ptx::tc_fence_after();
-                    {
-                        uint32_t u[32];
-                        float v[32];
-                        tmem_ld32(t_qkv, u);
-                        ptx::tmem_ld_wait();
-                        const float scale = 0.17677669529663687f;        // 32^-0.5, reference :325
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
+                    for (int part = 0; part < 4; ++part) {       // q dims 0-15, 16-31, k dims 0-15, 16-31
+                        uint32_t u[16];
+                        float v[16];
+                        tmem_ld16(t_qkv + 16u * (uint32_t)part, u);
+                        ptx::tmem_ld_wait();
+                        const float scale = part < 2 ? 0.17677669529663687f : 1.f;       // q * 32^-0.5 (reference :325); k unscaled
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
                             const float x0 = __uint_as_float(u[2 * i]) * scale, y0 = __uint_as_float(u[2 * i + 1]) * scale;
-                            v[2 * i] = x0 * rc[i] - y0 * rs[i];
-                            v[2 * i + 1] = y0 * rc[i] + x0 * rs[i];
+                            const float cc = rc[8 * (part & 1) + i], sn = rs[8 * (part & 1) + i];
+                            v[2 * i] = x0 * cc - y0 * sn;
+                            v[2 * i + 1] = y0 * cc + x0 * sn;
                         }
-                        store_hilo_row(smem + OFF_Q, r, v);
-                        if (a.dbg && my_grow >= 0) {
+                        store_hilo_half(sb + (part < 2 ? OFF_Q : OFF_K), r, part & 1, v);
+                        if (DBG) {
+                            if (a.dbg && my_grow >= 0) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) a.dbg[my_grow * dbg_ld + h * 32 + i] = v[i];
-                        }
-                        tmem_ld32(t_qkv + 32, u);
-                        ptx::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float x0 = __uint_as_float(u[2 * i]), y0 = __uint_as_float(u[2 * i + 1]);
-                            v[2 * i] = x0 * rc[i] - y0 * rs[i];
-                            v[2 * i + 1] = y0 * rc[i] + x0 * rs[i];
-                        }
-                        store_hilo_row(smem + OFF_K, r, v);
-                        if (a.dbg && my_grow >= 0) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) a.dbg[my_grow * dbg_ld + hid + h * 32 + i] = v[i];
+                                for (int i = 0; i < 16; ++i) a.dbg[my_grow * dbg_ld + (part < 2 ? 0 : hid) + h * 32 + 16 * (part & 1) + i] = v[i];
+                            }
                         }
                     }
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
-                    ptx::mbar_arrive(bar_at(smem, B_QK_READY));
-                    ptx::mbar_arrive(bar_at(smem, B_QKV_EMPTY + b));
-                    // ---------- WG-A: softmax of this row's 40-column block ----------
-                    ptx::mbar_wait(bar_at(smem, B_S_FULL), gh & 1);
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::mbar_arrive(bar_at(smem, B_QK_READY));
+                        ptx::mbar_arrive(bar_at(smem, B_QKV_EMPTY));
+                    }
+                }
+            }
+        } else if (wg == 2) {
+            // ---------- WG-C: softmax rows ----------
+            uint32_t g = 0, it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                int64_t my_grow = -1;
+                if (DBG) {
+                    const int pc = tile * FG + rpx;
+                    if (row_real && pc < a.n_pc) my_grow = ((int64_t)(pc / a.pix) * FL + fr) * a.pix + (pc % a.pix);
+                }
+                for (int h = 0; h < heads; ++h, ++g) {
+                    ptx::mbar_wait(bar_at(smem, B_S_FULL + (g & 1)), (g >> 1) & 1);
                     ptx::tc_fence_after();
-                    float sv[FL];
-                    {
-                        const uint32_t t_s = lane_base + T_S;
-                        const bool use_hi = straddle && px != pxlo;
-#pragma unroll
-                        for (int c = 0; c < FL / 8; ++c) {       // 8 columns at a time keeps the live register set small
-                            uint32_t u0[8], u1[8];
-                            tmem_ld8(t_s + (uint32_t)(FL * pxlo + 8 * c), u0);
-                            if (straddle) tmem_ld8(t_s + (uint32_t)(FL * pxhi + 8 * c), u1);
-                            ptx::tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) sv[8 * c + j] = __uint_as_float(use_hi ? u1[j] : u0[j]);
-                        }
-                    }
-                    if (a.pos_bias) {      // T5 relative-position bias row (h, frame): 160 B, L1 / L2 resident
-                        const float4* bp = reinterpret_cast<const float4*>(a.pos_bias + ((int64_t)h * FL + fr) * FL);
-#pragma unroll
-                        for (int i = 0; i < FL / 4; ++i) {
-                            const float4 t4 = __ldg(bp + i);
-                            sv[4 * i] += t4.x; sv[4 * i + 1] += t4.y; sv[4 * i + 2] += t4.z; sv[4 * i + 3] += t4.w;
-                        }
-                    }
-                    float mx = sv[0];
-#pragma unroll
-                    for (int j = 1; j < FL; ++j) mx = fmaxf(mx, sv[j]);
-                    float sum = 0.f;
-#pragma unroll
-                    for (int j = 0; j < FL; ++j) { sv[j] = __expf(sv[j] - mx); sum += sv[j]; }
-                    const float inv = 1.f / sum;
-#pragma unroll
-                    for (int j = 0; j < FL; ++j) sv[j] *= inv;
-                    if (a.dbg && my_grow >= 0) {
-#pragma unroll
-                        for (int j = 0; j < FL; ++j) a.dbg[my_grow * dbg_ld + 3 * hid + h * FL + j] = sv[j];
-                    }
-#pragma unroll
-                    for (int c = 0; c < FL / 8; ++c) {
-                        uint4 hh, ll;
-                        split2(sv[8 * c], sv[8 * c + 1], hh.x, ll.x);
-                        split2(sv[8 * c + 2], sv[8 * c + 3], hh.y, ll.y);
-                        split2(sv[8 * c + 4], sv[8 * c + 5], hh.z, ll.z);
-                        split2(sv[8 * c + 6], sv[8 * c + 7], hh.w, ll.w);
-                        *reinterpret_cast<uint4*>(smem + OFF_P + sw_off(r, c)) = hh;
-                        *reinterpret_cast<uint4*>(smem + OFF_P + 16384 + sw_off(r, c)) = ll;
-                    }
-                    {   // positions 40..47 (third K-step reads them): zero; the hi-plane chunk was overwritten by the O tile
-                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                        *reinterpret_cast<uint4*>(smem + OFF_P + sw_off(r, FL / 8)) = z;
-                        *reinterpret_cast<uint4*>(smem + OFF_P + 16384 + sw_off(r, FL / 8)) = z;
-                    }
+                    softmax_row<DBG>(a, smem, sb, lane_base + T_S + 128u * (g & 1u), r, px, pxlo, pxhi, straddle, fr, h, g, h == 0 ? it : 0u,
+                                     my_grow, dbg_ld, hid);
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
-                    ptx::mbar_arrive(bar_at(smem, B_P_READY));
-                } else {
-                    // ---------- WG-B: v -> transposed compact operand ----------
-                    ptx::mbar_wait(bar_at(smem, B_QKV_FULL + b), (gh >> 1) & 1);
+                    warp_arrive(bar_at(smem, B_P_READY), lane);
+                }
+            }
+        } else {
+            // ---------- WG-B: v -> transposed compact operand; PV result -> O operand rows; tile epilogue ----------
+            const int t128 = tc & 127;
+            const int l16 = t128 & 15, rg = t128 >> 4;   // store mapping of the epilogue: 16 lanes per row, 8 rows per pass
+            uint32_t g = 0, it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                int64_t my_grow = -1;
+                if (DBG) {
+                    const int pc = tile * FG + rpx;
+                    if (row_real && pc < a.n_pc) my_grow = ((int64_t)(pc / a.pix) * FL + fr) * a.pix + (pc % a.pix);
+                }
+                for (int h = 0; h < heads; ++h, ++g) {
+                    const uint32_t t_qkv = lane_base + T_QKV;
+                    ptx::mbar_wait(bar_at(smem, B_QKV_FULL), g & 1);
                     ptx::tc_fence_after();
-                    {
-                        uint32_t u[32];
-                        tmem_ld32(t_qkv + 64, u);
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        uint32_t u[16];
+                        tmem_ld16(t_qkv + 64u + 16u * (uint32_t)part, u);
                         ptx::tmem_ld_wait();
                         if (row_real) {
-                            uint8_t* vt = smem + OFF_VT;
 #pragma unroll
-                            for (int d = 0; d < 32; ++d) {
-                                const float x0 = __uint_as_float(u[d]);
+                            for (int dd = 0; dd < 16; ++dd) {
+                                const int d = 16 * part + dd;
+                                const float x0 = __uint_as_float(u[dd]);
                                 const bf16 hi = __float2bfloat16_rn(x0);
                                 const bf16 lo = __float2bfloat16_rn(x0 - __bfloat162float(hi));
                                 const int n = px * 32 + d;
-                                const uint32_t off = sw_off(n, fr >> 3) + (uint32_t)((fr & 7) * 2);
-                                *reinterpret_cast<bf16*>(vt + off) = hi;
-                                *reinterpret_cast<bf16*>(vt + VT_PLANE + off) = lo;
+                                const uint32_t off = sb + OFF_VT + sw_off(n, fr >> 3) + (uint32_t)((fr & 7) * 2);
+                                sts16(off, *reinterpret_cast<const uint16_t*>(&hi));
+                                sts16(off + VT_PLANE, *reinterpret_cast<const uint16_t*>(&lo));
                             }
-                            if (a.dbg && my_grow >= 0) {
+                            if (DBG) {
+                                if (a.dbg && my_grow >= 0) {
 #pragma unroll
-                                for (int d = 0; d < 32; ++d) a.dbg[my_grow * dbg_ld + 2 * hid + h * 32 + d] = __uint_as_float(u[d]);
+                                    for (int dd = 0; dd < 16; ++dd) a.dbg[my_grow * dbg_ld + 2 * hid + h * 32 + 16 * part + dd] = __uint_as_float(u[dd]);
+                                }
                             }
                         }
                     }
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
-                    ptx::mbar_arrive(bar_at(smem, B_VT_READY));
-                    ptx::mbar_arrive(bar_at(smem, B_QKV_EMPTY + b));
-                    // ---------- WG-B: this row's 32 output columns -> O operand row ----------
-                    ptx::mbar_wait(bar_at(smem, B_PVD_FULL), gh & 1);
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::mbar_arrive(bar_at(smem, B_VT_READY));
+                        ptx::mbar_arrive(bar_at(smem, B_QKV_EMPTY));
+                    }
+                    // this row's 32 output columns -> O operand row
+                    ptx::mbar_wait(bar_at(smem, B_PVD_FULL), g & 1);
                     ptx::tc_fence_after();
                     {
-                        float v[32];
                         const bool use_hi = straddle && px != pxlo;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint32_t u0[8], u1[8];
-                            tmem_ld8(lane_base + T_PVD + (uint32_t)(32 * pxlo + 8 * c), u0);
-                            if (straddle) tmem_ld8(lane_base + T_PVD + (uint32_t)(32 * pxhi + 8 * c), u1);
-                            ptx::tmem_ld_wait();
+                        for (int half = 0; half < 2; ++half) {
+                            float v[16];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[8 * c + j] = __uint_as_float(use_hi ? u1[j] : u0[j]);
-                        }
-                        store_hilo_row(smem + OFF_P, r, v);
-                        if (a.dbg && my_grow >= 0) {
+                            for (int c = 0; c < 2; ++c) {
+                                uint32_t u0[8], u1[8];
+                                tmem_ld8(lane_base + T_PVD + (uint32_t)(32 * pxlo + 16 * half + 8 * c), u0);
+                                if (straddle) tmem_ld8(lane_base + T_PVD + (uint32_t)(32 * pxhi + 16 * half + 8 * c), u1);
+                                ptx::tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) a.dbg[my_grow * dbg_ld + 3 * hid + heads * FL + h * 32 + i] = v[i];
+                                for (int j = 0; j < 8; ++j) v[8 * c + j] = __uint_as_float(use_hi ? u1[j] : u0[j]);
+                            }
+                            store_hilo_half(sb + OFF_O, r, half, v);
+                            if (DBG) {
+                                if (a.dbg && my_grow >= 0) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) a.dbg[my_grow * dbg_ld + 3 * hid + heads * FL + h * 32 + 16 * half + i] = v[i];
+                                }
+                            }
                         }
                     }
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
-                    ptx::mbar_arrive(bar_at(smem, B_O_READY));
+                    warp_arrive(bar_at(smem, B_O_READY), lane);
                 }
-            }
-            g += (uint32_t)heads;
 
-            // ---------------- epilogue: OUT (+bias) + x -> global, coalesced through XR ----------------
-            ptx::mbar_wait(bar_at(smem, B_OUT_FULL), it & 1);
-            ptx::tc_fence_after();
-            {
-                uint32_t u[32];
-                tmem_ld32(lane_base + T_OUT + 32u * (uint32_t)wg, u);
-                ptx::tmem_ld_wait();
+                // ---------------- epilogue: OUT (+bias) + x -> global, coalesced through the P operand buffer ----------------
+                float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.out_bias) ob = __ldg(reinterpret_cast<const float4*>(a.out_bias + l16 * 4));
+                ptx::mbar_wait(bar_at(smem, B_OUT_FULL), it & 1);       // implies PV of the last head is done with P
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int part = 0; part < 4; ++part) {
+                    uint32_t u[16];
+                    tmem_ld16(lane_base + T_OUT + 16u * (uint32_t)part, u);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int lc = part * 4 + c;
+                        sts128(sb + OFF_P + (uint32_t)(r * 256 + ((lc ^ (r & 7)) << 4)), u[4 * c], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
+                    }
+                }
                 ptx::tc_fence_before();
-                ptx::mbar_arrive(bar_at(smem, B_OUT_EMPTY));
-                float4* row4 = reinterpret_cast<float4*>(xr) + r * 16;
+                warp_arrive(bar_at(smem, B_OUT_EMPTY), lane);
+                asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int lc = wg * 8 + c;
-                    float4 t4 = row4[lc ^ (r & 7)];
-                    t4.x += __uint_as_float(u[4 * c]); t4.y += __uint_as_float(u[4 * c + 1]);
-                    t4.z += __uint_as_float(u[4 * c + 2]); t4.w += __uint_as_float(u[4 * c + 3]);
-                    row4[lc ^ (r & 7)] = t4;
-                }
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int half = 0; half < 2; ++half) {
+                    float4 xres[8];
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const int row = p * 16 + rg;
-                const int tpx = row / FL, tf = row - tpx * FL;
-                const int pc = tile * FG + tpx;
-                if (row < FG * FL && pc < a.n_pc) {
-                    const int64_t gr = ((int64_t)(pc / a.pix) * FL + tf) * a.pix + (pc % a.pix);
-                    float4 t4 = reinterpret_cast<const float4*>(xr)[row * 16 + (l16 ^ (row & 7))];
-                    t4.x += ob.x; t4.y += ob.y; t4.z += ob.z; t4.w += ob.w;
-                    if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + gr * FC + l16 * 4) = t4;
-                    if (a.out_sb) store_sb4(a.out_sb, a.out_plane, gr * FC + l16 * 4, t4);
+                    for (int p = 0; p < 8; ++p) {
+                        const int row = (half * 8 + p) * 8 + rg;
+                        const int tpx = row / FL, tf = row - tpx * FL;
+                        const int pc = tile * FG + tpx;
+                        const bool ok = row < FG * FL && pc < a.n_pc;
+                        const int64_t grow = ok ? ((int64_t)(pc / a.pix) * FL + tf) * a.pix + (pc % a.pix) : 0;
+                        xres[p] = ok ? *reinterpret_cast<const float4*>(a.x + grow * FC + l16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const int row = (half * 8 + p) * 8 + rg;
+                        const int tpx = row / FL, tf = row - tpx * FL;
+                        const int pc = tile * FG + tpx;
+                        if (row < FG * FL && pc < a.n_pc) {
+                            const int64_t grow = ((int64_t)(pc / a.pix) * FL + tf) * a.pix + (pc % a.pix);
+                            float4 t4 = lds128f(sb + OFF_P + (uint32_t)(row * 256 + ((l16 ^ (row & 7)) << 4)));
+                            t4.x += xres[p].x + ob.x; t4.y += xres[p].y + ob.y; t4.z += xres[p].z + ob.z; t4.w += xres[p].w + ob.w;
+                            if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + grow * FC + l16 * 4) = t4;
+                            if (a.out_sb) store_sb4(a.out_sb, a.out_plane, grow * FC + l16 * 4, t4);
+                        }
+                    }
                 }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                // the staging tile overwrote P's zero pad (positions 40..47 = chunk 5 of both planes): restore it, then release P
+                sts128(sb + OFF_P + sw_off(r, 5), 0u, 0u, 0u, 0u);
+                sts128(sb + OFF_P + 16384 + sw_off(r, 5), 0u, 0u, 0u, 0u);
+                ptx::fence_proxy_async();
+                warp_arrive(bar_at(smem, B_STG_FREE), lane);
             }
         }
     }
@@ -580,7 +700,8 @@ int lfdm_attn_temporal_fused(const float* x, const float* gamma, const void* wq_
     static int sms[64] = {};
     if (dev < 0 || dev >= 64) return LFDM_E_UNSUPP;
     if (!attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(attn_temporal_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(attn_temporal_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_temporal_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (sms[dev] <= 0) sms[dev] = 148;
@@ -594,6 +715,9 @@ int lfdm_attn_temporal_fused(const float* x, const float* gamma, const void* wq_
     a.out_f32 = out_f32; a.out_sb = reinterpret_cast<bf16*>(out_sb); a.out_plane = out_plane; a.dbg = debug;
     a.heads = heads; a.n_pc = n_b * pixels; a.pix = pixels; a.n_tiles = (a.n_pc + FG - 1) / FG; a.eps = eps;
     const int grid = a.n_tiles < sms[dev] ? a.n_tiles : sms[dev];
-    LFDM_LAUNCH_PDL(attn_temporal_fused_kernel, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a);
+    if (debug)
+        LFDM_LAUNCH_PDL(attn_temporal_fused_kernel<true>, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a);
+    else
+        LFDM_LAUNCH_PDL(attn_temporal_fused_kernel<false>, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a);
     return 0;
 }

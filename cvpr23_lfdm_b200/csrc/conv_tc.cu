@@ -713,7 +713,11 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
         if (!d->a_sb[s] || (d->a_c[s] % BK) != 0) return LFDM_E_UNSUPP;
         if (reinterpret_cast<uintptr_t>(d->a_sb[s]) & 15) return LFDM_E_UNSUPP;
     }
-    if (d->reflect) return LFDM_E_UNSUPP;
+    // reflect padding (NATOPS up-sampling conv, reference :156-163): reflecting the x2 nearest up-sampled map by one pixel equals
+    // CLAMPING on the low-resolution map, so the caller hands in the replicate-padded input [(h_in+2) x (w_in+2)]
+    // (lfdm_pad_replicate_rows) and every tap coordinate shifts by +1: no out-of-bounds access remains.
+    if (d->reflect && d->mode != LFDM_CONV_UPNEAREST) return LFDM_E_UNSUPP;
+    const int rpad = d->reflect ? 1 : 0;
     const int cin_total = d->a_c[0] + d->a_c[1];
 
     // ---- iteration geometry (the grid the M tiles walk) and per-launch tap lists
@@ -769,8 +773,9 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
                 cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bnf, 1};
                 rc = make_map(&a.tmA[s * 4 + v], base + ((int64_t)ph * W + pw) * C, 5, dims, strides, box);
             } else {
-                cuuint64_t dims[5] = {C, W, H, (cuuint64_t)d->nf, 2};
-                cuuint64_t strides[4] = {C * 2, W * C * 2, H * W * C * 2, (cuuint64_t)d->a_plane[src] * 2};
+                const cuuint64_t Wp = W + 2 * rpad, Hp = H + 2 * rpad;
+                cuuint64_t dims[5] = {C, Wp, Hp, (cuuint64_t)d->nf, 2};
+                cuuint64_t strides[4] = {C * 2, Wp * C * 2, Hp * Wp * C * 2, (cuuint64_t)d->a_plane[src] * 2};
                 cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bnf, 1};
                 rc = make_map(&a.tmA[s * 4 + v], base, 5, dims, strides, box);
             }
@@ -875,7 +880,7 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
                 dyl[0] = p ? 0 : -1; dyl[1] = p ? 1 : 0;
                 dxl[0] = qq ? 0 : -1; dxl[1] = qq ? 1 : 0;
             }
-            for (int t = 0; t < 4; ++t) { a.tap_map[t] = 0; a.tap_dy[t] = (int8_t)dyl[t >> 1]; a.tap_dx[t] = (int8_t)dxl[t & 1]; }
+            for (int t = 0; t < 4; ++t) { a.tap_map[t] = 0; a.tap_dy[t] = (int8_t)(dyl[t >> 1] + rpad); a.tap_dx[t] = (int8_t)(dxl[t & 1] + rpad); }
         }
         int rc;
         const int n_kb = taps_per_launch * (a.chunks[0] + a.chunks[1]);

@@ -330,6 +330,23 @@ __global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ ou
         store_sb1(out, plane, i, in[i]);
 }
 
+// SB rows [n][h][w][c] -> replicate-padded SB rows [n][h+2][w+2][c] (16-byte chunks of both planes)
+__global__ void pad_replicate_kernel(const uint4* __restrict__ in, int64_t in_plane16, uint4* __restrict__ out, int64_t out_plane16,
+                                     int n, int h, int w, int c8) {
+    const int64_t total = (int64_t)n * (h + 2) * (w + 2) * c8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % c8);
+        int64_t p = i / c8;
+        const int x = (int)(p % (w + 2)); p /= (w + 2);
+        const int y = (int)(p % (h + 2));
+        const int64_t img = p / (h + 2);
+        const int sx = min(max(x - 1, 0), w - 1), sy = min(max(y - 1, 0), h - 1);
+        const int64_t src = ((img * h + sy) * w + sx) * c8 + q;
+        out[i] = in[src];
+        out[out_plane16 + i] = in[in_plane16 + src];
+    }
+}
+
 inline int grid_for(int64_t total, int cap = 148 * 32) {
     int64_t b = (total + 255) / 256;
     if (b > cap) b = cap;
@@ -442,6 +459,16 @@ extern "C" int lfdm_unet_heads_cfg(const float* a, const float* wa, const float*
                                    float* out, void* stream) {
     if (b < 1) return LFDM_E_BADARG;
     return unet_heads_launch(a, wa, ba, na, o, wo, bo, no, c, b, f, p, out, (int64_t)b * f * p, cond_scale, stream);
+}
+
+extern "C" int lfdm_pad_replicate_rows(const void* in_sb, int64_t in_plane, void* out_sb, int64_t out_plane, int n, int h, int w,
+                                       int c, void* stream) {
+    if (!in_sb || !out_sb || (c & 7) || (in_plane & 7) || (out_plane & 7)) return LFDM_E_BADARG;
+    const int64_t total = (int64_t)n * (h + 2) * (w + 2) * (c / 8);
+    pad_replicate_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)in_sb, in_plane / 8, (uint4*)out_sb,
+                                                                            out_plane / 8, n, h, w, c / 8);
+    LFDM_CHECK_LAUNCH();
+    return 0;
 }
 
 extern "C" int lfdm_split_bf16(const float* in, void* out_sb, int64_t out_plane, int64_t n, void* stream) {

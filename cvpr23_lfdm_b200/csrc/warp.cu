@@ -160,6 +160,119 @@ __global__ void __launch_bounds__(256) warp_rows_kernel(const float* __restrict_
     }
 }
 
+// Batched variant for the channel counts of the decoder (c = 64 / 128 / 256): LPP lanes sweep one pixel with QPL float4 each
+// and U pixel slots are processed together -- all 4*U*QPL tap loads and the U*QPL `prev` loads of a lane are issued before the
+// first use, so a warp keeps >= 20 independent 16-byte loads in flight (the plain kernel above issues one pixel's loads, waits,
+// stores, and is latency-bound at ~45 % of the HBM peak).
+__device__ __forceinline__ float4 ldg_nc4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+template <int LPP, int QPL, int U>
+__global__ void __launch_bounds__(256) warp_rows_batched_kernel(const float* __restrict__ src, const float* __restrict__ flow,
+                                                                const float* __restrict__ occ, const float* __restrict__ prev,
+                                                                float* __restrict__ out_f32, bf16* __restrict__ out_sb,
+                                                                int64_t out_plane, const float* __restrict__ sb_scale,
+                                                                const float* __restrict__ sb_shift, int sb_act, int64_t n_img,
+                                                                int frames_per_src, int hs, int ws, int hf, int wf) {
+    constexpr int C = LPP * QPL * 4;
+    constexpr int PPI = 32 / LPP;                            // pixels per slot row
+    const int lane = threadIdx.x & 31;
+    const int64_t total_pix = n_img * hs * ws;
+    const int64_t n_groups = (total_pix + 31) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int hw = hs * ws;
+    const int sub = lane / LPP, ql = lane - sub * LPP;
+    float4 sc4[QPL], sh4[QPL];
+#pragma unroll
+    for (int qq = 0; qq < QPL; ++qq) {
+        sc4[qq] = sb_scale ? *reinterpret_cast<const float4*>(sb_scale + (ql + qq * LPP) * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+        sh4[qq] = sb_shift ? *reinterpret_cast<const float4*>(sb_shift + (ql + qq * LPP) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int64_t g = warp0; g < n_groups; g += nwarps) {
+        // ---- phase 1: per-pixel set-up (lane = pixel)
+        const int64_t pix = (g << 5) + lane;
+        int off[4] = {-1, -1, -1, -1};
+        float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+        float oc = 1.f;
+        if (pix < total_pix) {
+            const int n = (int)(pix / hw);
+            const int rem = (int)(pix - (int64_t)n * hw);
+            const int y = rem / ws, x = rem - y * ws;
+            float gx, gy;
+            latent_at(flow, occ, n, y, x, hs, ws, hf, wf, gx, gy, oc);
+            const Taps t = make_taps(gx, gy, hs, ws);
+            const int sbase = (n / frames_per_src) * hw;
+            if (t.vy0 && t.vx0) off[0] = sbase + t.y0 * ws + t.x0;
+            if (t.vy0 && t.vx1) off[1] = sbase + t.y0 * ws + t.x1;
+            if (t.vy1 && t.vx0) off[2] = sbase + t.y1 * ws + t.x0;
+            if (t.vy1 && t.vx1) off[3] = sbase + t.y1 * ws + t.x1;
+            wgt[0] = t.wnw; wgt[1] = t.wne; wgt[2] = t.wsw; wgt[3] = t.wse;
+        }
+        // ---- phase 2: U pixel slots at a time
+#pragma unroll 1
+        for (int it = 0; it < 32; it += PPI * U) {
+            int o[U][4];
+            float w[U][4], ocp[U];
+            bool live[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int pl = it + u * PPI + sub;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    o[u][k] = __shfl_sync(0xffffffffu, off[k], pl);
+                    w[u][k] = __shfl_sync(0xffffffffu, wgt[k], pl);
+                }
+                ocp[u] = __shfl_sync(0xffffffffu, oc, pl);
+                live[u] = ((g << 5) + pl) < total_pix;
+            }
+            float4 tap[U][QPL][4], pv[U][QPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int qq = 0; qq < QPL; ++qq) {
+                    const int q4 = (ql + qq * LPP) * 4;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tap[u][qq][k] = (live[u] && o[u][k] >= 0) ? ldg_nc4(src + (int64_t)o[u][k] * C + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    pv[u][qq] = (live[u] && prev && occ) ? ldg_nc4(prev + ((g << 5) + it + u * PPI + sub) * C + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!live[u]) continue;
+                const int64_t p = (g << 5) + it + u * PPI + sub;
+#pragma unroll
+                for (int qq = 0; qq < QPL; ++qq) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc = fma4(acc, tap[u][qq][k], w[u][k]);     // invalid taps hold zeros (same sums as the plain kernel)
+                    float4 r;
+                    if (occ) {
+                        r = make_float4(acc.x * ocp[u], acc.y * ocp[u], acc.z * ocp[u], acc.w * ocp[u]);
+                        if (prev) {
+                            const float om = 1.f - ocp[u];
+                            r.x += pv[u][qq].x * om; r.y += pv[u][qq].y * om; r.z += pv[u][qq].z * om; r.w += pv[u][qq].w * om;
+                        }
+                    } else {
+                        r = acc;
+                    }
+                    const int64_t oidx = p * C + (ql + qq * LPP) * 4;
+                    if (out_f32) *reinterpret_cast<float4*>(out_f32 + oidx) = r;
+                    if (out_sb) {
+                        float4 t4 = r;
+                        if (sb_scale) { t4.x *= sc4[qq].x; t4.y *= sc4[qq].y; t4.z *= sc4[qq].z; t4.w *= sc4[qq].w; }
+                        if (sb_shift) { t4.x += sh4[qq].x; t4.y += sh4[qq].y; t4.z += sh4[qq].z; t4.w += sh4[qq].w; }
+                        store_sb4(out_sb, out_plane, oidx,
+                                  make_float4(apply_act(t4.x, sb_act), apply_act(t4.y, sb_act), apply_act(t4.z, sb_act), apply_act(t4.w, sb_act)));
+                    }
+                }
+            }
+        }
+    }
+}
+
 // 3-channel planar image: one thread per output pixel
 __global__ void __launch_bounds__(256) warp_image_kernel(const float* __restrict__ src, const float* __restrict__ flow,
                                                          const float* __restrict__ occ, const float* __restrict__ prev,
@@ -204,9 +317,21 @@ extern "C" int lfdm_warp_blend_rows(const float* src, const float* flow, const f
     int64_t blocks = (groups + 7) / 8;                  // 8 warps per block, one 32-pixel group per warp iteration
     if (blocks > 148 * 16) blocks = 148 * 16;
     if ((int64_t)n * hs * ws >= (1ll << 31) / 1 || (int64_t)(n / frames_per_src + 1) * hs * ws >= (1ll << 31)) return LFDM_E_BADARG;
+    static const bool plain_env = (getenv("LFDM_WARP_PLAIN") != nullptr);       // A/B switch: one pixel slot at a time
+    const bool plain = plain_env || (prev && (const void*)prev == (const void*)out_f32);   // in-place blend: no read-only path for prev
+    const bool al16 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(prev) | reinterpret_cast<uintptr_t>(sb_scale) |
+                        reinterpret_cast<uintptr_t>(sb_shift)) & 15) == 0;
+#define LFDM_WARP_BATCHED(LPP, QPL, U)                                                                                       \
+    warp_rows_batched_kernel<LPP, QPL, U><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                                 \
+        src, flow, occ, prev, out_f32, (bf16*)out_sb, out_plane, sb_scale, sb_shift, sb_act, n, frames_per_src, hs, ws, hf, wf)
+    if (!plain && al16 && c == 64) LFDM_WARP_BATCHED(16, 1, 4);
+    else if (!plain && al16 && c == 128) LFDM_WARP_BATCHED(32, 1, 4);
+    else if (!plain && al16 && c == 256) LFDM_WARP_BATCHED(32, 2, 2);
+    else
     warp_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, flow, occ, prev, out_f32, (bf16*)out_sb,
                                                                         out_plane, sb_scale, sb_shift, sb_act, n,
                                                                         frames_per_src, hs, ws, c, hf, wf);
+#undef LFDM_WARP_BATCHED
     LFDM_CHECK_LAUNCH();
     return 0;
 }

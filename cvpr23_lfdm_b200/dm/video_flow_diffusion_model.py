@@ -74,6 +74,13 @@ class FlowDiffusion(nn.Module):
         self.sample_out_vid, self.sample_warped_vid = self.generator.decode_video(
             self.sample_img, self.sample_vid_grid, self.sample_vid_conf)
 
+    def render_sample_panels(self, index=0, mean=(0.0, 0.0, 0.0)):
+        """Extension: the uint8 5-panel frames demo_mug.py:126-145 builds on the host with numpy +
+        matplotlib + PIL, composed on the GPU -> (F, H, 5W, 3) uint8 CUDA tensor (see cvpr23_lfdm_b200/output.py)."""
+        from ..output import render_panels
+        return render_panels(self.sample_img, self.sample_out_vid, self.sample_warped_vid, self.sample_vid_grid,
+                             self.sample_vid_conf, index=index, mean=mean)
+
     # ---- real-video branch (reference :116-143): pseudo ground-truth flow of a driving video ----------
     def set_train_input(self, ref_img, real_vid, ref_text):
         self.ref_img, self.real_vid, self.ref_text = ref_img.cuda(), real_vid.cuda(), ref_text

@@ -77,7 +77,9 @@ class ConvLayer:
             self.w_plane = self.w_sb[0].numel()
 
     def _tc_static_ok(self):
-        if self.reflect or any(c % 64 for c in self.src_channels) or len(self.src_channels) > 2:
+        if any(c % 64 for c in self.src_channels) or len(self.src_channels) > 2:
+            return False
+        if self.reflect and not (self.mode == L.CONV_UPNEAREST and len(self.src_channels) == 1):
             return False
         if not (self.cout % 32 == 0 or self.cout <= 16):
             return False
@@ -121,6 +123,13 @@ class ConvLayer:
                 a_f32[i] = s
                 all_sb = False
         fused_stats = gn_stats is not None and FUSED_GN_STATS
+        if self.reflect and self.w_sb is not None and all_sb:
+            # tcgen05 engine: reflect padding of the x2 nearest up-sampled map == clamping on the low-res map -> replicate-pad once
+            src = srcs[0]
+            padded = SB(nf * (h + 2) * (w + 2), src.c, src.t.device)
+            check(lib().lfdm_pad_replicate_rows(ptr(src.t), src.plane, ptr(padded.t), padded.plane, nf, h, w, src.c, stream()),
+                  "lfdm_pad_replicate_rows")
+            a_sb[0], a_plane[0] = padded.t, padded.plane
         kw = dict(a_sb=a_sb, a_f32=a_f32, a_plane=a_plane, a_c=a_c, nf=nf, h_in=h, w_in=w, h_out=ho, w_out=wo,
                   kh=self.kh, kw=self.kw, pad=self.pad, stride=self.stride, mode=self.mode, reflect=self.reflect,
                   w_f32=self.w_f32, w_sb=self.w_sb, w_plane=self.w_plane if self.w_sb is not None else 0,

@@ -59,7 +59,9 @@ typedef struct lfdm_conv_desc {
     int32_t      h_out, w_out;
     int32_t      kh, kw, pad, stride;
     int32_t      mode;         /* LFDM_CONV_*                                                                 */
-    int32_t      reflect;      /* 1: reflect padding (padding_mode='reflect', video_flow_diffusion.py:162)    */
+    int32_t      reflect;      /* 1: reflect padding (padding_mode='reflect', video_flow_diffusion.py:162).  TC engine:
+                                  LFDM_CONV_UPNEAREST only, and a_sb must then be the REPLICATE-PADDED input
+                                  [(h_in+2) x (w_in+2)] from lfdm_pad_replicate_rows (reflect on the x2 map == clamp here) */
     /* weights */
     const float* w_f32;        /* SIMT: [kh*kw][Cin_total][Cout]                                              */
     const void*  w_sb;         /* TC  : packed by lfdm_pack, hi plane                         */
@@ -179,6 +181,9 @@ int lfdm_from_rows(const float* rows, int ld, int b, int c, int f, int p, float*
 /* 7x7 (k x k) im2col of a few-channel planar tensor in[b][c][f][h][w] -> SB rows [M][k_pad], k = tap*c + ch      */
 int lfdm_im2col_small(const float* in, int b, int c, int f, int h, int w, int ksize, int pad, int k_pad,
                       void* out_sb, int64_t out_plane, void* stream);
+/* SB rows [n][h][w][c] -> SB rows [n][h+2][w+2][c] with replicated borders (operand of the reflect-padded up-sampling conv) */
+int lfdm_pad_replicate_rows(const void* in_sb, int64_t in_plane, void* out_sb, int64_t out_plane, int n, int h, int w, int c,
+                            void* stream);
 /* 2x2 average pool on rows (DownBlock2d, util.py:124,131)                                                        */
 int lfdm_avgpool2_rows(const float* in, int n, int h, int w, int c, float* out_f32, void* out_sb, int64_t out_plane,
                        void* stream);
@@ -210,6 +215,17 @@ int lfdm_motion_finish(const float* logits, int ld, const float* sparse, int n, 
                        float* flow, float* occ, void* stream);
 /* per-image mean over positions of a row matrix [N*p][c] -> [N][c] (bg_motion_predictor.py:47)                    */
 int lfdm_rows_mean(const float* rows, int n, int p, int c, float* out, void* stream);
+
+/* --- output stage (demo/demo_mug.py:126-145) --------------------------------------------------------------- */
+/* uint8 5-panel frames of ONE sample: out[f][H][5W][3] = [source | generated | warped source | sampling-grid figure | confidence].
+ * src (3,H,W); out_vid / warped_vid (3,F,H,W); grid (2,F,h,w) absolute sampling grid in [-1,1]; conf (1,F,h,w) (device pointers);
+ * mean3: HOST pointer to the 3 per-channel means already divided by 255 (demo MEAN / 255), or NULL.
+ * Photographic panels: clamp(x + mean, 0, 1) * 255 truncated (sample_img :68-74); confidence: nearest up-sampling of conf * 255
+ * truncated (misc.conf2fig); grid panel: identity grid + warped grid polylines, anti-aliased (replaces misc.grid2fig's matplotlib
+ * figure: visually equivalent, not pixel-identical).  workspace: >= f*4*4 (rounded up to 256 B) + f*2*H*W*4 bytes.            */
+int lfdm_render_panels(const float* src, const float* out_vid, const float* warped_vid, const float* grid, const float* conf,
+                       const float* mean3, int f, int H, int W, int h, int w, float line_width, void* workspace, uint8_t* out,
+                       void* stream);
 
 /* --- weight packing (host-side helper, device pointers) ------------------------------------------------------ */
 /* fp32 [rows][cols] -> SB planes                                                                                 */

@@ -11,9 +11,23 @@ RTOL, ATOL = 1e-3, 1e-4
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+_LOG = None
+
+
+@pytest.fixture(autouse=True)
+def _record_errors(parity_log):
+    """every close() of this module also records its measured error (-> profiles/r02_parity_errors.md)"""
+    global _LOG
+    _LOG = parity_log
+    yield
+    _LOG = None
+
+
 def close(a, b, what, rtol=RTOL, atol=ATOL):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     assert a.shape == b.shape, (what, a.shape, b.shape)
+    if _LOG is not None:
+        _LOG(what, a, b, tol=[rtol, atol])
     err = (a - b).abs()
     bad = (err > atol + rtol * b.abs()).sum().item()
     assert bad == 0, f"{what}: {bad}/{a.numel()} out of tolerance; max abs err {err.max().item():.3e}; ref rms {b.pow(2).mean().sqrt().item():.3e}"
