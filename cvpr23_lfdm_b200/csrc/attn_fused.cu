@@ -28,6 +28,8 @@
 //   epilogue:   (WG-B) OUT (+bias) + x -> F32 and split-bf16 rows, coalesced through the (then idle) P operand buffer.
 // Synchronisation: mbarriers (tcgen05.commit for MMA completion, one elected arrival per warp) + one named barrier
 // (epilogue).  Shared memory is addressed with explicit st.shared / ld.shared on 32-bit addresses.
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -77,9 +79,16 @@ struct FusedArgs {
     bf16* out_sb;
     int64_t out_plane;
     float* dbg;                  // diagnostics (tests): [M][3*hid + heads*40 + hid] or null
+    long long* trace;            // LFDM_ATTN_TRACE=1: [32 event slots][64 heads] clock64() stamps of CTA 0 (pipeline timeline)
     int32_t heads, n_pc, pix, n_tiles;
     float eps;
 };
+
+// timeline stamp of event `slot` for flat head index g (CTA 0 only; `who` = the one thread of the role that stamps)
+#define TR(slot, g, who)                                                                             \
+    do {                                                                                             \
+        if (a.trace && blockIdx.x == 0 && (who) && (g) < 64u) a.trace[(slot) * 64 + (g)] = clock64(); \
+    } while (0)
 
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -215,8 +224,10 @@ __device__ __forceinline__ void softmax_row(const FusedArgs& a, uint8_t* smem, u
     }
     // P is single-buffered: PV of the previous head must have read it (its scores were computed ahead of it), and on the first
     // head of a tile the epilogue of the previous tile must have released the buffer it uses as its staging tile
+    TR(14, g, r == 0);
     if (g > 0) ptx::mbar_wait(bar_at(smem, B_PVD_FULL), (g - 1) & 1);
     if (stg_it > 0) ptx::mbar_wait(bar_at(smem, B_STG_FREE), (stg_it - 1) & 1);
+    TR(15, g, r == 0);
 #pragma unroll
     for (int c = 0; c < FL / 8; ++c) {
         uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
@@ -315,10 +326,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
             uint32_t q_it = 0; int q_h = 0;                  // cursor of issue_qkv
             auto issue_qkv = [&](uint32_t gq) {
                 const int s = gq & 1;                         // weight ring stage
+                TR(0, gq, true);
                 if (q_h == 0) ptx::mbar_wait(bar_at(smem, B_XN_FULL), q_it & 1);      // this tile's LayerNorm operand is in place
                 ptx::mbar_wait(bar_at(smem, B_WQ_FULL + s), (gq >> 1) & 1);
                 ptx::mbar_wait(bar_at(smem, B_QKV_EMPTY), (gq & 1) ^ 1);             // q | k | v of head gq-1 have been read
                 ptx::tc_fence_after();
+                TR(1, gq, true);
                 const uint32_t td = tmem_base + T_QKV;
                 const uint64_t w_hi = d_wq + (uint64_t)((s * WQ_STAGE) >> 4), w_lo = w_hi + (uint64_t)(12288 >> 4);
                 const uint64_t x_hi = d_xn, x_lo = d_xn + (uint64_t)(16384 >> 4);
@@ -339,8 +352,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
             auto issue_qk = [&](uint32_t gk) {
                 // S[gk & 1] = Q K^T : rows [hi | lo]: K-steps 0,1 = hi dims, 2,3 = lo dims.  The buffer was last read by the
                 // softmax of head gk-2, whose P_READY this thread has already waited for.
+                TR(2, gk, true);
                 ptx::mbar_wait(bar_at(smem, B_QK_READY), gk & 1);
                 ptx::tc_fence_after();
+                TR(3, gk, true);
                 const uint32_t td = tmem_base + T_S + 128u * (gk & 1u);
                 ptx::umma_bf16(td, d_q + 4, d_k + 0, ID128, 0u);      // q_lo . k_hi
                 ptx::umma_bf16(td, d_q + 6, d_k + 2, ID128, 1u);
@@ -359,9 +374,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
             for (uint32_t g = 0; g < NG; ++g) {
                 if (g + 1 < NG) issue_qk(g + 1);             // next head's scores while the softmax of head g is running
                 // ---- D = P V : compact K = 48 positions; D column block 32*pixel
+                TR(4, g, true);
                 ptx::mbar_wait(bar_at(smem, B_P_READY), g & 1);
+                TR(22, g, true);
                 ptx::mbar_wait(bar_at(smem, B_VT_READY), g & 1);
                 ptx::tc_fence_after();
+                TR(5, g, true);
                 {
                     const uint32_t td = tmem_base + T_PVD;
                     const uint64_t p_hi = d_p, p_lo = d_p + (uint64_t)(16384 >> 4);
@@ -381,10 +399,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                 if (!last_head && g + 2 < NG) issue_qkv(g + 2);
                 // ---- OUT += O_h Wout_h^T
                 const int so = g & 1;
+                TR(6, g, true);
                 ptx::mbar_wait(bar_at(smem, B_O_READY), g & 1);
                 ptx::mbar_wait(bar_at(smem, B_WO_FULL + so), (g >> 1) & 1);
                 if (h == 0) ptx::mbar_wait(bar_at(smem, B_OUT_EMPTY), (it & 1) ^ 1);
                 ptx::tc_fence_after();
+                TR(7, g, true);
                 {
                     const uint32_t td = tmem_base + T_OUT;
                     const uint64_t w = d_wo + (uint64_t)((so * WO_STAGE) >> 4);
@@ -486,9 +506,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                 }
                 for (int h = 0; h < heads; ++h, ++g) {
                     const uint32_t t_qkv = lane_base + T_QKV;
+                    TR(8, g, r == 0);
                     ptx::mbar_wait(bar_at(smem, B_QKV_FULL), g & 1);
+                    TR(9, g, r == 0);
                     if (g > 0) ptx::mbar_wait(bar_at(smem, B_S_FULL + ((g - 1) & 1)), ((g - 1) >> 1) & 1);   // QK(g-1) is done with Q / K
                     ptx::tc_fence_after();
+                    TR(10, g, r == 0);
 #pragma unroll
                     for (int part = 0; part < 4; ++part) {       // q dims 0-15, 16-31, k dims 0-15, 16-31
                         uint32_t u[16];
@@ -518,6 +541,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                         ptx::mbar_arrive(bar_at(smem, B_QK_READY));
                         ptx::mbar_arrive(bar_at(smem, B_QKV_EMPTY));
                     }
+                    TR(11, g, r == 0);
                 }
             }
         } else if (wg == 2) {
@@ -530,13 +554,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                     if (row_real && pc < a.n_pc) my_grow = ((int64_t)(pc / a.pix) * FL + fr) * a.pix + (pc % a.pix);
                 }
                 for (int h = 0; h < heads; ++h, ++g) {
+                    TR(12, g, r == 0);
                     ptx::mbar_wait(bar_at(smem, B_S_FULL + (g & 1)), (g >> 1) & 1);
                     ptx::tc_fence_after();
+                    TR(13, g, r == 0);
                     softmax_row<DBG>(a, smem, sb, lane_base + T_S + 128u * (g & 1u), r, px, pxlo, pxhi, straddle, fr, h, g, h == 0 ? it : 0u,
                                      my_grow, dbg_ld, hid);
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
                     warp_arrive(bar_at(smem, B_P_READY), lane);
+                    TR(16, g, r == 0);
                 }
             }
         } else {
@@ -552,8 +579,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                 }
                 for (int h = 0; h < heads; ++h, ++g) {
                     const uint32_t t_qkv = lane_base + T_QKV;
+                    TR(17, g, r == 0);
                     ptx::mbar_wait(bar_at(smem, B_QKV_FULL), g & 1);
                     ptx::tc_fence_after();
+                    TR(18, g, r == 0);
 #pragma unroll
                     for (int part = 0; part < 2; ++part) {
                         uint32_t u[16];
@@ -587,8 +616,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                         ptx::mbar_arrive(bar_at(smem, B_QKV_EMPTY));
                     }
                     // this row's 32 output columns -> O operand row
+                    TR(19, g, r == 0);
                     ptx::mbar_wait(bar_at(smem, B_PVD_FULL), g & 1);
                     ptx::tc_fence_after();
+                    TR(20, g, r == 0);
                     {
                         const bool use_hi = straddle && px != pxlo;
 #pragma unroll
@@ -615,6 +646,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
                     warp_arrive(bar_at(smem, B_O_READY), lane);
+                    TR(21, g, r == 0);
                 }
 
                 // ---------------- epilogue: OUT (+bias) + x -> global, coalesced through the P operand buffer ----------------
@@ -713,6 +745,8 @@ int lfdm_attn_temporal_fused(const float* x, const float* gamma, const void* wq_
     a.wq = reinterpret_cast<const uint8_t*>(wq_packed); a.wo = reinterpret_cast<const uint8_t*>(wo_packed);
     a.out_bias = out_bias; a.rot_cos = rot_cos; a.rot_sin = rot_sin; a.pos_bias = pos_bias;
     a.out_f32 = out_f32; a.out_sb = reinterpret_cast<bf16*>(out_sb); a.out_plane = out_plane; a.dbg = debug;
+    static const bool trace_mode = (getenv("LFDM_ATTN_TRACE") != nullptr);     // `debug` is then a [32][64] int64 stamp buffer
+    if (trace_mode && debug) { a.trace = reinterpret_cast<long long*>(debug); a.dbg = nullptr; debug = nullptr; }
     a.heads = heads; a.n_pc = n_b * pixels; a.pix = pixels; a.n_tiles = (a.n_pc + FG - 1) / FG; a.eps = eps;
     const int grid = a.n_tiles < sms[dev] ? a.n_tiles : sms[dev];
     if (debug)

@@ -91,9 +91,12 @@ class GeneratorEngine:
         dev = self.device
         # the encoder output of the last image is kept: sample_one_video calls compute_fea and then decode_video on the same
         # tensor (the reference re-runs the encoder once more per decoded frame, video_flow_diffusion_model.py:206-214)
-        ckey = (img.data_ptr(), img._version, tuple(img.shape), img.dtype)
-        if self._enc_cache is not None and self._enc_cache[0] == ckey:
-            return self._enc_cache[1]
+        # Keyed on the tensor OBJECT (kept alive by the cache) + its version counter: an address-based key would hit on a new
+        # image that the allocator placed at a freed image's address.
+        src_img = img
+        hit = self._enc_cache
+        if hit is not None and hit[0] is src_img and hit[1] == src_img._version:
+            return hit[2]
         img = img.float().contiguous()
         b, c, h, w = img.shape
         m = b * h * w
@@ -114,7 +117,7 @@ class GeneratorEngine:
                   "lfdm_avgpool2_rows")
             skips.append((p, co, ch, cw))
             x_sb = p_sb
-        self._enc_cache = (ckey, skips)
+        self._enc_cache = (src_img, src_img._version, skips)
         return skips
 
     def compute_fea(self, img):

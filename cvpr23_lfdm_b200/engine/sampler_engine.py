@@ -151,10 +151,10 @@ class SamplerEngine:
         key = (id(eng), tuple(shape), guided, float(cond_scale) if guided else 1.0, tuple(times), tuple(draw_noise),
                bool(clip_denoised), coef.data_ptr())
         st = self._loops.get(key)
-        if st is None or st["eng"] is not eng:
+        if st is None or st["eng"] is not eng or st["coef"] is not coef:      # `coef` is pinned by the entry: no address reuse
             if len(self._loops) >= 2:           # each entry pins one step's activation pool: keep at most two
                 self._loops.clear()
-            st = {"eng": eng, "graph": None, "img": torch.empty(shape, device=dev), "noise": torch.empty(shape, device=dev),
+            st = {"eng": eng, "coef": coef, "graph": None, "img": torch.empty(shape, device=dev), "noise": torch.empty(shape, device=dev),
                   "step_idx": torch.zeros((1,), dtype=torch.int32, device=dev), "fea_conv": None, "cond_tab": None,
                   "x2": torch.empty((2 * b,) + tuple(shape[1:]), device=dev) if guided else None}
             self._loops[key] = st

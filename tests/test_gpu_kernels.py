@@ -159,7 +159,7 @@ TC_CASES = [
     dict(n=3, cins=[64], cout=64, h=16, w=8, k=3, pad=1),                                         # halo mode, bw=8 bh=16
     dict(n=2, cins=[64], cout=128, h=64, w=32, k=3, pad=1, residual=True),                        # halo mode, 16 row tiles
     dict(n=2, cins=[64], cout=64, h=16, w=16, k=3, pad=1, mode=2, reflect=True),                  # NATOPS up-conv: reflect == clamp on the low-res map
-    dict(n=3, cins=[256], cout=256, h=4, w=4, k=3, pad=1, mode=2, reflect=True, f32_act=1),       # ... 4x4 -> 8x8, BN=128
+    dict(n=8, cins=[256], cout=256, h=4, w=4, k=3, pad=1, mode=2, reflect=True, f32_act=1),       # ... 4x4 -> 8x8, BN=128 (8 frames per 128-row tile)
 ]
 
 
