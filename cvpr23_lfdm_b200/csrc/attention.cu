@@ -931,12 +931,12 @@ __global__ void __launch_bounds__(128, 4) attn_softmax_mma16v2_kernel(const floa
 }
 
 inline int v2_set_smem(size_t smem) {
-    static bool done = false;
-    if (!done) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(attn_softmax_mma16v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_softmax_mma16v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        done = true;
+        once.mark();
     }
     return 0;
 }
@@ -1277,12 +1277,12 @@ static int launch_attn_softmax(const float* qkv, void* out_sb, int64_t out_plane
     int wpb = (int)(100 * 1024 / per_warp);
     if (wpb > 4) wpb = 4;
     if (wpb < 1) wpb = 1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(attn_softmax_kernel<RIP, CJ, ALIAS_P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(per_warp * 4 > 200 * 1024 ? 200 * 1024 : per_warp * 4));
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        once.mark();
     }
     const int64_t units = n_seq * heads;
     const int64_t blocks = (units + wpb - 1) / wpb;
@@ -1322,11 +1322,11 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
         }
         if (use_mma && !use_tf32) {
             const size_t smem = sizeof(float) * 4 * (2 * ML * QP2 + ML * VP2);
-            static bool attr16 = false;
-            if (!attr16) {
+            static PerDeviceOnce once16;
+            if (once16.need()) {
                 cudaError_t e = cudaFuncSetAttribute(attn_softmax_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return (int)e;
-                attr16 = true;
+                once16.mark();
             }
             const int64_t units = n_seq * heads;
             LFDM_LAUNCH_PDL(attn_softmax_mma16_kernel, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
@@ -1336,11 +1336,11 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
         }
         if (use_mma) {
             const size_t smem = sizeof(float) * 4 * (2 * ML * QP + ML * VPM);
-            static bool attr_set = false;
-            if (!attr_set) {
+            static PerDeviceOnce once;
+            if (once.need()) {
                 cudaError_t e = cudaFuncSetAttribute(attn_softmax_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return (int)e;
-                attr_set = true;
+                once.mark();
             }
             const int64_t units = n_seq * heads;
             attn_softmax_mma_kernel<<<(unsigned)((units + 3) / 4), 128, smem, st>>>(
@@ -1380,12 +1380,12 @@ extern "C" int lfdm_attn_linear(const float* qkv, void* out_sb, int64_t out_plan
                                 int n_pos, int heads, void* stream) {
     if (!qkv || n_pos <= 0 || heads <= 0) return LFDM_E_BADARG;
     const size_t smem = sizeof(float) * LW * 4 * TILE;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(attn_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        once.mark();
     }
     static const bool use_mma = (getenv("LFDM_ATTN_SIMT") == nullptr);          // A/B switch: CUDA-core tiling instead
     if (use_mma)

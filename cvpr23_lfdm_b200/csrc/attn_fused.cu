@@ -5,29 +5,34 @@
 // Replaces Residual(PreNorm(EinopsToAndFrom(Attention))) of the reference (DM/modules/video_flow_diffusion.py:132-138,
 // 170-190, 270-283, 286-363) for C = 64 channels and 40 frames (the 32x32 / 16x16 levels: init_temporal_attn, downs.0,
 // ups.2, ups.3).  q|k|v, the scores and the per-head outputs never leave the SM: the four GEMM-shaped stages run on
-// tcgen05 with fp32 accumulators in TMEM, everything between them is done by two warp-groups straight out of TMEM.
+// tcgen05 with fp32 accumulators in TMEM, everything between them is done by three warp-groups straight out of TMEM.
 //
-// One tile = 3 pixel columns x 40 frames = 120 rows of the row matrix (padded to the 128-row UMMA tile).  Roles:
-//   warp 0      MMA issuer (one elected thread), software-pipelined over the flat (tile, head) sequence:
-//                 QK(g+1) -> PV(g) -> qkv(g+2) -> out(g)         (scores double-buffered in TMEM: QK(g+1) runs while the
-//                 softmax of head g is still reading S(g); qkv runs ahead, also across tiles)
-//   warp 1      weight producer: per head one [W_hi|W_lo] slice of to_qkv (24 KiB) and of to_out (8 KiB), pre-swizzled on
-//               the host, cp.async.bulk from L2 into 2-stage rings
-//   warps 2-3   LayerNorm producers: the NEXT tile's x rows are loaded into registers while the current tile is being
-//               processed; as soon as the last qkv GEMM of the current tile has drained the operand buffer they normalise
-//               and write the split-bf16 A operand (128x64, SW128 K-major)
-//   warps 4-7   WG-A: q*scale, rotary(q), rotary(k) TMEM -> [hi|lo] operand rows
-//   warps 8-11  WG-B: v TMEM -> transposed compact B operand V^T[(pixel, d)][j]; PV result -> [hi|lo] operand rows of the
-//               output projection
-//   warps 12-15 WG-C: +bias, softmax over the row's 40 columns, P -> compact A operand [128 x 48] (hi / lo planes)
-//               (the three groups work on different heads at the same time: conversion(g+1) | softmax(g) | output(g-1))
-//   per head:   qkv  D[128x96]   = Xn . W_h^T          3 split-bf16 products x 4 K-steps, double-buffered TMEM
+// One tile = 3 pixel columns x 40 frames = 120 rows of the row matrix (padded to the 128-row UMMA tile); per head:
+//               qkv  D[128x96]   = Xn . W_h^T          3 split-bf16 products x 4 K-steps, double-buffered in TMEM
 //               QK   S[128x128]  = Q . K^T             all 3 pixels at once; a row only uses its own 40-column block
 //               PV   D[128x96]   = P . V^T^T           compact K = 48 positions; column block 32*pixel(row) is the result
 //               out  OUT[128x64] += O_h . Wout_h^T     accumulated over heads in TMEM
-//   epilogue:   (WG-B) OUT (+bias) + x -> F32 and split-bf16 rows, coalesced through the (then idle) P operand buffer.
-// Synchronisation: mbarriers (tcgen05.commit for MMA completion, one elected arrival per warp) + one named barrier
-// (epilogue).  Shared memory is addressed with explicit st.shared / ld.shared on 32-bit addresses.
+// The kernel is a DATAFLOW pipeline over the flat (tile, head) sequence g.  Measured history (tools/attn_trace.py stamps every
+// barrier crossing of CTA 0 with clock64()): one blocking in-order issue thread + single-buffered V^T: 5.8 k clk per head and
+// 29 k clk per tile boundary (0.77 ms per 32x32 block at batch 8); MMAs issued by lanes of the compute groups: the spinning
+// sibling lanes steal the issue slots (1 k clk per 6 MMAs); thread-per-row epilogue: 32 lines per store instruction, every
+// st.shared of the SM stalls behind it for 17 k clk per tile.  Current roles (18 warps):
+//   warp 0      MMA issuer (one elected thread) POLLING four independent streams -- qkv(g) into T_QKV[g & 1], QK(g), PV(g),
+//               out(g) -- with non-blocking mbarrier tests, downstream first: no stage waits behind an unrelated one
+//   warp 1      weight producer: per head one [W_hi|W_lo] slice of to_qkv (24 KiB) and of to_out (8 KiB, two heads later),
+//               pre-swizzled on the host, cp.async.bulk from L2 into 2-stage rings
+//   warps 2-5   LayerNorm producers + tile epilogue: the NEXT tile's x rows are loaded and normalised in registers while the
+//               current tile is being processed; once the last qkv GEMM of the current tile has drained the operand buffer
+//               they split and store the A operand (128x64, SW128 K-major, hi / lo planes); then OUT (+bias) + x of the
+//               previous tile -> F32 and split-bf16 rows straight from TMEM, coalesced by a 4x4 chunk transpose inside
+//               every lane quad (shuffles)
+//   warps 6-9   WG-A: rotary(q) (scale folded into W_q), rotary(k) TMEM -> [hi|lo] operand rows
+//   warps 10-13 WG-B: PV(g) result -> [hi|lo] operand rows of the output projection (downstream first), then v(g+2) -> the
+//               MN-major B operand V[(g+2) & 1][position][(pixel, d)]: 64 contiguous bytes per thread instead of 64 two-byte
+//               scatter stores of the transposed K-major form (kept behind LFDM_ATTN_VT_KMAJOR=1 as a cross-check)
+//   warps 14-17 WG-C: +bias, softmax over the row's 40 columns, P -> compact A operand [128 x 48] (hi / lo planes)
+// Synchronisation: mbarriers only (tcgen05.commit for MMA completion, one elected arrival per warp).  Shared memory is
+// addressed with explicit st.shared / ld.shared on 32-bit addresses.
 #include <cstdlib>
 #include <cstring>
 #include "common.cuh"
@@ -38,32 +43,36 @@ namespace {
 constexpr int FL = 40;       // frames (sequence length)
 constexpr int FG = 3;        // pixel columns per tile
 constexpr int FC = 64;       // channels
-constexpr int NTHREADS = 512;
+constexpr int NTHREADS = 576;       // 18 warps (register cap 112)
 
 constexpr int OFF_XN = 0;            // 2 planes x 16 KiB : LayerNorm output, A operand of the qkv GEMM
 constexpr int OFF_Q = 32768;         // 16 KiB : rows [q_hi(32) | q_lo(32)]
 constexpr int OFF_K = 49152;         // 16 KiB : rows [k_hi | k_lo]
-constexpr int OFF_VT = 65536;        // 2 planes x 12 KiB : V^T, 96 rows (pixel, d) x 64 positions (48 used)
+constexpr int OFF_VT = 65536;        // 2 buffers x 2 planes x 12 KiB : V^T, 96 rows (pixel, d) x 64 positions (48 used)
 constexpr int VT_PLANE = 12288;
-constexpr int OFF_P = 90112;         // 2 planes x 16 KiB : P rows x 64 positions (48 used, 40..47 zero); fp32 staging tile of the epilogue
-constexpr int OFF_O = 122880;        // 16 KiB : rows [o_hi(32) | o_lo(32)]
-constexpr int OFF_WQ = 139264;       // 2 stages x 24 KiB : [W_hi (96 x 64) | W_lo (96 x 64)] of one head
+constexpr int VT_BUF = 24576;
+constexpr int OFF_P = 114688;        // 2 planes x 16 KiB : P rows x 64 positions (48 used, 40..47 zero); fp32 staging tile of the epilogue
+constexpr int OFF_O = 147456;        // 16 KiB : rows [o_hi(32) | o_lo(32)]
+constexpr int OFF_WQ = 163840;       // 2 stages x 24 KiB : [W_hi (96 x 64) | W_lo (96 x 64)] of one head
 constexpr int WQ_STAGE = 24576;
-constexpr int OFF_WO = 188416;       // 2 stages x 8 KiB : 64 rows [w_hi(32) | w_lo(32)] of one head
+constexpr int OFF_WO = 212992;       // 2 stages x 8 KiB : 64 rows [w_hi(32) | w_lo(32)] of one head
 constexpr int WO_STAGE = 8192;
-constexpr int OFF_BAR = 204800;      // mbarriers, TMEM pointer
-constexpr int SMEM_BYTES = OFF_BAR + 1024 + 1024;
+constexpr int OFF_BAR = 229376;      // mbarriers, TMEM pointer
+constexpr int OFF_INV = OFF_BAR + 1024;   // 2 x 128 floats: 1 / (softmax denominator) of every tile row, per head parity
+constexpr int SMEM_BYTES = OFF_INV + 1024 + 1024;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KiB per CTA)");
 
-// TMEM column map (512 columns allocated)
-constexpr uint32_t T_QKV = 0;        // 96
-constexpr uint32_t T_S = 96;         // 2 x 128 (double-buffered scores)
-constexpr uint32_t T_PVD = 352;      // 96
+// TMEM column map (512 columns)
+constexpr uint32_t T_QKV = 0;        // 2 x 96 (double-buffered q | k | v of one head)
+constexpr uint32_t T_S = 192;        // 128
+constexpr uint32_t T_PVD = 320;      // 128 (96 used with the K-major V^T operand, 128 = two 64-wide atoms with the MN-major V operand)
 constexpr uint32_t T_OUT = 448;      // 64
+constexpr int VMN_ATOM = 6144;       // MN-major V operand: one 64-column atom = 48 positions x 128 B
 
 enum {
-    B_XN_FULL = 0, B_XN_EMPTY = 1, B_WQ_FULL = 2, B_WQ_EMPTY = 4, B_WO_FULL = 6, B_WO_EMPTY = 8, B_QKV_FULL = 10,
-    B_QKV_EMPTY = 11, B_QK_READY = 12, B_S_FULL = 13 /* 2 */, B_P_READY = 16, B_VT_READY = 17, B_PVD_FULL = 18, B_O_READY = 19,
-    B_OUT_FULL = 20, B_OUT_EMPTY = 21, B_STG_FREE = 22
+    B_XN_FULL = 0, B_XN_EMPTY = 1, B_WQ_FULL = 2 /* 2 */, B_WQ_EMPTY = 4 /* 2 */, B_WO_FULL = 6 /* 2 */, B_WO_EMPTY = 8 /* 2 */,
+    B_QKV_FULL = 10 /* 2 */, B_QKV_EMPTY = 12 /* 2 */, B_S_FULL = 14, B_S_EMPTY = 15, B_VT_READY = 16 /* 2 */, B_PVD_FULL = 18,
+    B_PVD_EMPTY = 19, B_O_FREE = 20, B_OUT_FULL = 21, B_OUT_EMPTY = 22, B_QK_READY = 23, B_P_READY = 24, B_O_READY = 25
 };
 
 struct FusedArgs {
@@ -95,6 +104,20 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
                      ptx::smem_u32(smem_dst)),
                  "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(ptx::smem_u32(bar))
                  : "memory");
+}
+// non-blocking phase test (the issuer polls several independent streams)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(ptx::smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -172,75 +195,12 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
     if (lane == 0) ptx::mbar_arrive(bar);
 }
 
-// softmax over the 40 columns of row r (TMEM block at column 40*pixel) -> normalised probabilities as split-bf16 chunks 0..4
-template <bool DBG>
-__device__ __forceinline__ void softmax_row(const FusedArgs& a, uint8_t* smem, uint32_t sb, uint32_t t_s, int r, int px, int pxlo,
-                                            int pxhi, bool straddle, int fr, int h, uint32_t g, uint32_t stg_it, int64_t my_grow,
-                                            int dbg_ld, int hid) {
-    constexpr float L2E = 1.4426950408889634f;
-    float sv[FL];
-    {
-        const bool use_hi = straddle && px != pxlo;
-#pragma unroll
-        for (int c = 0; c < FL / 8; ++c) {       // 8 columns at a time keeps the live register set small
-            uint32_t u0[8], u1[8];
-            tmem_ld8(t_s + (uint32_t)(FL * pxlo + 8 * c), u0);
-            if (straddle) tmem_ld8(t_s + (uint32_t)(FL * pxhi + 8 * c), u1);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sv[8 * c + j] = __uint_as_float(use_hi ? u1[j] : u0[j]);
-        }
-    }
-    if (a.pos_bias) {      // T5 relative-position bias row (h, frame): L1 / L2 resident
-        const float4* bp = reinterpret_cast<const float4*>(a.pos_bias + ((int64_t)h * FL + fr) * FL);
-#pragma unroll
-        for (int i = 0; i < FL / 4; ++i) {
-            const float4 t4 = __ldg(bp + i);
-            sv[4 * i] += t4.x; sv[4 * i + 1] += t4.y; sv[4 * i + 2] += t4.z; sv[4 * i + 3] += t4.w;
-        }
-    }
-    float m0 = fmaxf(sv[0], sv[1]), m1 = fmaxf(sv[2], sv[3]), m2 = fmaxf(sv[4], sv[5]), m3 = fmaxf(sv[6], sv[7]);
-#pragma unroll
-    for (int j = 8; j < FL; j += 4) {
-        m0 = fmaxf(m0, sv[j]); m1 = fmaxf(m1, sv[j + 1]); m2 = fmaxf(m2, sv[j + 2]); m3 = fmaxf(m3, sv[j + 3]);
-    }
-    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-    const float nb = -mx * L2E;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int j = 0; j < FL; j += 4) {
-        sv[j] = ex2(fmaf(sv[j], L2E, nb)); sv[j + 1] = ex2(fmaf(sv[j + 1], L2E, nb));
-        sv[j + 2] = ex2(fmaf(sv[j + 2], L2E, nb)); sv[j + 3] = ex2(fmaf(sv[j + 3], L2E, nb));
-        s0 += sv[j]; s1 += sv[j + 1]; s2 += sv[j + 2]; s3 += sv[j + 3];
-    }
-    const float inv = 1.f / ((s0 + s1) + (s2 + s3));
-#pragma unroll
-    for (int j = 0; j < FL; ++j) sv[j] *= inv;
-    if (DBG) {
-        if (a.dbg && my_grow >= 0) {
-#pragma unroll
-            for (int j = 0; j < FL; ++j) a.dbg[my_grow * dbg_ld + 3 * hid + h * FL + j] = sv[j];
-        }
-    }
-    // P is single-buffered: PV of the previous head must have read it (its scores were computed ahead of it), and on the first
-    // head of a tile the epilogue of the previous tile must have released the buffer it uses as its staging tile
-    TR(14, g, r == 0);
-    if (g > 0) ptx::mbar_wait(bar_at(smem, B_PVD_FULL), (g - 1) & 1);
-    if (stg_it > 0) ptx::mbar_wait(bar_at(smem, B_STG_FREE), (stg_it - 1) & 1);
-    TR(15, g, r == 0);
-#pragma unroll
-    for (int c = 0; c < FL / 8; ++c) {
-        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-        split2(sv[8 * c], sv[8 * c + 1], h0, l0);
-        split2(sv[8 * c + 2], sv[8 * c + 3], h1, l1);
-        split2(sv[8 * c + 4], sv[8 * c + 5], h2, l2);
-        split2(sv[8 * c + 6], sv[8 * c + 7], h3, l3);
-        sts128(sb + OFF_P + sw_off(r, c), h0, h1, h2, h3);
-        sts128(sb + OFF_P + 16384 + sw_off(r, c), l0, l1, l2, l3);
-    }
-}
+// named barrier of one compute warp-group (ids 1..3), 128 threads
+__device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-template <bool DBG>
+// VMN: v is stored as an MN-major B operand [position][(pixel, d)] (64 contiguous bytes per thread) instead of the
+// K-major transposed V^T[(pixel, d)][position] (64 two-byte scatter stores per thread)
+template <bool DBG, bool VMN>
 __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const __grid_constant__ FusedArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -252,25 +212,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
 
     pdl_trigger();
     if (warp == 1 && ptx::elect_one()) {
-        ptx::mbar_init(bar_at(smem, B_XN_FULL), 2);
+        ptx::mbar_init(bar_at(smem, B_XN_FULL), 4);
         ptx::mbar_init(bar_at(smem, B_XN_EMPTY), 1);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(bar_at(smem, B_WQ_FULL + i), 1);
             ptx::mbar_init(bar_at(smem, B_WQ_EMPTY + i), 1);
             ptx::mbar_init(bar_at(smem, B_WO_FULL + i), 1);
             ptx::mbar_init(bar_at(smem, B_WO_EMPTY + i), 1);
-            ptx::mbar_init(bar_at(smem, B_S_FULL + i), 1);
+            ptx::mbar_init(bar_at(smem, B_QKV_FULL + i), 1);
+            ptx::mbar_init(bar_at(smem, B_QKV_EMPTY + i), 8);
+            ptx::mbar_init(bar_at(smem, B_VT_READY + i), 4);
         }
-        ptx::mbar_init(bar_at(smem, B_QKV_FULL), 1);
-        ptx::mbar_init(bar_at(smem, B_QKV_EMPTY), 8);
-        ptx::mbar_init(bar_at(smem, B_QK_READY), 4);
-        ptx::mbar_init(bar_at(smem, B_STG_FREE), 4);
-        ptx::mbar_init(bar_at(smem, B_P_READY), 4);
-        ptx::mbar_init(bar_at(smem, B_VT_READY), 4);
+        ptx::mbar_init(bar_at(smem, B_S_FULL), 1);
+        ptx::mbar_init(bar_at(smem, B_S_EMPTY), 4);
         ptx::mbar_init(bar_at(smem, B_PVD_FULL), 1);
-        ptx::mbar_init(bar_at(smem, B_O_READY), 4);
+        ptx::mbar_init(bar_at(smem, B_PVD_EMPTY), 4);
+        ptx::mbar_init(bar_at(smem, B_O_FREE), 1);
         ptx::mbar_init(bar_at(smem, B_OUT_FULL), 1);
         ptx::mbar_init(bar_at(smem, B_OUT_EMPTY), 4);
+        ptx::mbar_init(bar_at(smem, B_QK_READY), 4);
+        ptx::mbar_init(bar_at(smem, B_P_READY), 4);
+        ptx::mbar_init(bar_at(smem, B_O_READY), 4);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -290,189 +252,299 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
     const int n_tiles = a.n_tiles;
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t NG = (uint32_t)(my_tiles * heads);        // flat (tile, head) sequence of this CTA
+    const uint32_t sb = ptx::smem_u32(smem);
 
     if (warp == 1) {
         // ===================== weight producer =====================
+        // to_out slices trail the to_qkv slices by two heads: out(g) runs ~3 head periods after qkv(g), and waiting here for
+        // out(g-2) before fetching W_qkv(g+1) would tie the head of the pipeline to its tail
         if (ptx::elect_one()) {
-            int h = 0;
-            for (uint32_t g = 0; g < NG; ++g) {
-                const int s = g & 1;
-                const uint32_t par = ((g >> 1) & 1) ^ 1;
-                ptx::mbar_wait(bar_at(smem, B_WQ_EMPTY + s), par);
-                ptx::mbar_arrive_expect_tx(bar_at(smem, B_WQ_FULL + s), WQ_STAGE);
-                bulk_copy_g2s(smem + OFF_WQ + s * WQ_STAGE, a.wq + (size_t)h * WQ_STAGE, WQ_STAGE, bar_at(smem, B_WQ_FULL + s));
-                ptx::mbar_wait(bar_at(smem, B_WO_EMPTY + s), par);
-                ptx::mbar_arrive_expect_tx(bar_at(smem, B_WO_FULL + s), WO_STAGE);
-                bulk_copy_g2s(smem + OFF_WO + s * WO_STAGE, a.wo + (size_t)h * WO_STAGE, WO_STAGE, bar_at(smem, B_WO_FULL + s));
-                if (++h == heads) h = 0;
+            int h = 0, ho = 0;
+            for (uint32_t g = 0; g < NG + 2; ++g) {
+                if (g < NG) {
+                    const int s = g & 1;
+                    ptx::mbar_wait(bar_at(smem, B_WQ_EMPTY + s), ((g >> 1) & 1) ^ 1);
+                    ptx::mbar_arrive_expect_tx(bar_at(smem, B_WQ_FULL + s), WQ_STAGE);
+                    bulk_copy_g2s(smem + OFF_WQ + s * WQ_STAGE, a.wq + (size_t)h * WQ_STAGE, WQ_STAGE, bar_at(smem, B_WQ_FULL + s));
+                    if (++h == heads) h = 0;
+                }
+                if (g >= 2) {
+                    const uint32_t go = g - 2;
+                    const int s = go & 1;
+                    ptx::mbar_wait(bar_at(smem, B_WO_EMPTY + s), ((go >> 1) & 1) ^ 1);
+                    ptx::mbar_arrive_expect_tx(bar_at(smem, B_WO_FULL + s), WO_STAGE);
+                    bulk_copy_g2s(smem + OFF_WO + s * WO_STAGE, a.wo + (size_t)ho * WO_STAGE, WO_STAGE, bar_at(smem, B_WO_FULL + s));
+                    if (++ho == heads) ho = 0;
+                }
             }
         }
     } else if (warp == 0) {
         // ===================== MMA issuer (one elected thread) =====================
+        // Four independent streams (qkv, QK, PV, out), each with its own cursor; the thread POLLS their input barriers and
+        // issues whichever is ready, downstream first: a stage never waits behind an unrelated one (a blocking in-order issue
+        // loop measured 5.8 k clk per head; issuing from lanes of the compute groups steals their issue slots).
         if (ptx::elect_one()) {
-            const uint32_t sb = ptx::smem_u32(smem);
             const uint64_t d_xn = ptx::make_sw128_kmajor_desc(sb + OFF_XN);
+            const uint64_t d_wq = ptx::make_sw128_kmajor_desc(sb + OFF_WQ);
             const uint64_t d_q = ptx::make_sw128_kmajor_desc(sb + OFF_Q);
             const uint64_t d_k = ptx::make_sw128_kmajor_desc(sb + OFF_K);
-            const uint64_t d_vt = ptx::make_sw128_kmajor_desc(sb + OFF_VT);
             const uint64_t d_p = ptx::make_sw128_kmajor_desc(sb + OFF_P);
+            const uint64_t d_vt = ptx::make_sw128_kmajor_desc(sb + OFF_VT);
             const uint64_t d_o = ptx::make_sw128_kmajor_desc(sb + OFF_O);
-            const uint64_t d_wq = ptx::make_sw128_kmajor_desc(sb + OFF_WQ);
             const uint64_t d_wo = ptx::make_sw128_kmajor_desc(sb + OFF_WO);
+            // MN-major, 128-byte-swizzled B operand: 64 columns (128 B) contiguous, 8 positions per 1024-byte group (SBO), the
+            // second 64-column atom VMN_ATOM bytes further (LBO)
+            const uint64_t d_vmn = (uint64_t)(((sb + OFF_VT) & 0x3FFFFu) >> 4) | ((uint64_t)(VMN_ATOM >> 4) << 16) |
+                                   ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             constexpr uint32_t ID96 = ptx::make_idesc_bf16(128, 96);
             constexpr uint32_t ID128 = ptx::make_idesc_bf16(128, 128);
+            constexpr uint32_t ID128T = ptx::make_idesc_bf16(128, 128) | (1u << 16);       // B operand MN-major
             constexpr uint32_t ID64 = ptx::make_idesc_bf16(128, 64);
-            // flat index g -> (tile iteration, head) without divisions: the three cursors advance monotonically
-            uint32_t q_it = 0; int q_h = 0;                  // cursor of issue_qkv
-            auto issue_qkv = [&](uint32_t gq) {
-                const int s = gq & 1;                         // weight ring stage
-                TR(0, gq, true);
-                if (q_h == 0) ptx::mbar_wait(bar_at(smem, B_XN_FULL), q_it & 1);      // this tile's LayerNorm operand is in place
-                ptx::mbar_wait(bar_at(smem, B_WQ_FULL + s), (gq >> 1) & 1);
-                ptx::mbar_wait(bar_at(smem, B_QKV_EMPTY), (gq & 1) ^ 1);             // q | k | v of head gq-1 have been read
-                ptx::tc_fence_after();
-                TR(1, gq, true);
-                const uint32_t td = tmem_base + T_QKV;
-                const uint64_t w_hi = d_wq + (uint64_t)((s * WQ_STAGE) >> 4), w_lo = w_hi + (uint64_t)(12288 >> 4);
-                const uint64_t x_hi = d_xn, x_lo = d_xn + (uint64_t)(16384 >> 4);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t o = (uint64_t)(ks * 2);
-                    ptx::umma_bf16(td, x_lo + o, w_hi + o, ID96, ks > 0 ? 1u : 0u);
-                    ptx::umma_bf16(td, x_hi + o, w_lo + o, ID96, 1u);
-                    ptx::umma_bf16(td, x_hi + o, w_hi + o, ID96, 1u);
-                }
-                ptx::umma_commit(bar_at(smem, B_WQ_EMPTY + s));
-                ptx::umma_commit(bar_at(smem, B_QKV_FULL));
-                if (++q_h == heads) {                       // last qkv GEMM of the tile: the operand buffer may be refilled
-                    ptx::umma_commit(bar_at(smem, B_XN_EMPTY));
-                    q_h = 0; ++q_it;
-                }
-            };
-            auto issue_qk = [&](uint32_t gk) {
-                // S[gk & 1] = Q K^T : rows [hi | lo]: K-steps 0,1 = hi dims, 2,3 = lo dims.  The buffer was last read by the
-                // softmax of head gk-2, whose P_READY this thread has already waited for.
-                TR(2, gk, true);
-                ptx::mbar_wait(bar_at(smem, B_QK_READY), gk & 1);
-                ptx::tc_fence_after();
-                TR(3, gk, true);
-                const uint32_t td = tmem_base + T_S + 128u * (gk & 1u);
-                ptx::umma_bf16(td, d_q + 4, d_k + 0, ID128, 0u);      // q_lo . k_hi
-                ptx::umma_bf16(td, d_q + 6, d_k + 2, ID128, 1u);
-                ptx::umma_bf16(td, d_q + 0, d_k + 4, ID128, 1u);      // q_hi . k_lo
-                ptx::umma_bf16(td, d_q + 2, d_k + 6, ID128, 1u);
-                ptx::umma_bf16(td, d_q + 0, d_k + 0, ID128, 1u);      // q_hi . k_hi
-                ptx::umma_bf16(td, d_q + 2, d_k + 2, ID128, 1u);
-                ptx::umma_commit(bar_at(smem, B_S_FULL + (gk & 1)));
-            };
-            if (NG > 0) {
-                issue_qkv(0);
-                issue_qk(0);
-                if (NG > 1) issue_qkv(1);
-            }
-            uint32_t it = 0; int h = 0;
-            for (uint32_t g = 0; g < NG; ++g) {
-                if (g + 1 < NG) issue_qk(g + 1);             // next head's scores while the softmax of head g is running
-                // ---- D = P V : compact K = 48 positions; D column block 32*pixel
-                TR(4, g, true);
-                ptx::mbar_wait(bar_at(smem, B_P_READY), g & 1);
-                TR(22, g, true);
-                ptx::mbar_wait(bar_at(smem, B_VT_READY), g & 1);
-                ptx::tc_fence_after();
-                TR(5, g, true);
+            uint32_t gq = 0, gk = 0, gv = 0, go = 0;     // next head of each stream
+            uint32_t it_q = 0, it_o = 0;
+            int h_q = 0, h_o = 0;
+            while (go < NG) {
+                bool issued = false;
+                // ---- OUT += O_h Wout_h^T
                 {
-                    const uint32_t td = tmem_base + T_PVD;
-                    const uint64_t p_hi = d_p, p_lo = d_p + (uint64_t)(16384 >> 4);
-                    const uint64_t v_hi = d_vt, v_lo = d_vt + (uint64_t)(VT_PLANE >> 4);
-#pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) {
-                        const uint64_t o = (uint64_t)(ks * 2);
-                        ptx::umma_bf16(td, p_lo + o, v_hi + o, ID96, ks > 0 ? 1u : 0u);
-                        ptx::umma_bf16(td, p_hi + o, v_lo + o, ID96, 1u);
-                        ptx::umma_bf16(td, p_hi + o, v_hi + o, ID96, 1u);
+                    const uint32_t so = go & 1u;
+                    if (mbar_test(bar_at(smem, B_O_READY), go & 1) && mbar_test(bar_at(smem, B_WO_FULL + so), (go >> 1) & 1) &&
+                        (h_o != 0 || it_o == 0 || mbar_test(bar_at(smem, B_OUT_EMPTY), (it_o - 1) & 1))) {
+                        ptx::tc_fence_after();
+                        TR(7, go, true);
+                        const uint32_t td = tmem_base + T_OUT;
+                        const uint64_t w = d_wo + (uint64_t)((so * WO_STAGE) >> 4);
+                        ptx::umma_bf16(td, d_o + 4, w + 0, ID64, h_o > 0 ? 1u : 0u);   // o_lo . w_hi
+                        ptx::umma_bf16(td, d_o + 6, w + 2, ID64, 1u);
+                        ptx::umma_bf16(td, d_o + 0, w + 4, ID64, 1u);               // o_hi . w_lo
+                        ptx::umma_bf16(td, d_o + 2, w + 6, ID64, 1u);
+                        ptx::umma_bf16(td, d_o + 0, w + 0, ID64, 1u);               // o_hi . w_hi
+                        ptx::umma_bf16(td, d_o + 2, w + 2, ID64, 1u);
+                        ptx::umma_commit(bar_at(smem, B_WO_EMPTY + so));
+                        ptx::umma_commit(bar_at(smem, B_O_FREE));
+                        if (++h_o == heads) { ptx::umma_commit(bar_at(smem, B_OUT_FULL)); h_o = 0; ++it_o; }
+                        ++go;
+                        issued = true;
                     }
                 }
-                ptx::umma_commit(bar_at(smem, B_PVD_FULL));
-                const bool last_head = (h == heads - 1);
-                // qkv(g+2) needs v of head g+1 scattered by WG-B; on a tile's last head WG-B first runs the epilogue, which waits
-                // for OUT_FULL: there the output projection goes first
-                if (!last_head && g + 2 < NG) issue_qkv(g + 2);
-                // ---- OUT += O_h Wout_h^T
-                const int so = g & 1;
-                TR(6, g, true);
-                ptx::mbar_wait(bar_at(smem, B_O_READY), g & 1);
-                ptx::mbar_wait(bar_at(smem, B_WO_FULL + so), (g >> 1) & 1);
-                if (h == 0) ptx::mbar_wait(bar_at(smem, B_OUT_EMPTY), (it & 1) ^ 1);
-                ptx::tc_fence_after();
-                TR(7, g, true);
-                {
-                    const uint32_t td = tmem_base + T_OUT;
-                    const uint64_t w = d_wo + (uint64_t)((so * WO_STAGE) >> 4);
-                    ptx::umma_bf16(td, d_o + 4, w + 0, ID64, h > 0 ? 1u : 0u);   // o_lo . w_hi
-                    ptx::umma_bf16(td, d_o + 6, w + 2, ID64, 1u);
-                    ptx::umma_bf16(td, d_o + 0, w + 4, ID64, 1u);               // o_hi . w_lo
-                    ptx::umma_bf16(td, d_o + 2, w + 6, ID64, 1u);
-                    ptx::umma_bf16(td, d_o + 0, w + 0, ID64, 1u);               // o_hi . w_hi
-                    ptx::umma_bf16(td, d_o + 2, w + 2, ID64, 1u);
+                // ---- D = P V : compact K = 48 positions; D column block 32*pixel
+                if (gv < NG) {
+                    const uint32_t s = gv & 1u;
+                    if (mbar_test(bar_at(smem, B_P_READY), gv & 1) && mbar_test(bar_at(smem, B_VT_READY + s), (gv >> 1) & 1) &&
+                        (gv == 0 || mbar_test(bar_at(smem, B_PVD_EMPTY), (gv - 1) & 1))) {
+                        ptx::tc_fence_after();
+                        TR(5, gv, true);
+                        const uint32_t td = tmem_base + T_PVD;
+                        const uint64_t p_hi = d_p, p_lo = d_p + (uint64_t)(16384 >> 4);
+                        if (VMN) {
+                            const uint64_t v_hi = d_vmn + (uint64_t)((s * VT_BUF) >> 4), v_lo = v_hi + (uint64_t)(VT_PLANE >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < 3; ++ks) {
+                                const uint64_t o = (uint64_t)(ks * 2), ov = (uint64_t)(ks * (2048 >> 4));   // 16 positions = 2 row groups
+                                ptx::umma_bf16(td, p_lo + o, v_hi + ov, ID128T, ks > 0 ? 1u : 0u);
+                                ptx::umma_bf16(td, p_hi + o, v_lo + ov, ID128T, 1u);
+                                ptx::umma_bf16(td, p_hi + o, v_hi + ov, ID128T, 1u);
+                            }
+                        } else {
+                            const uint64_t v_hi = d_vt + (uint64_t)((s * VT_BUF) >> 4), v_lo = v_hi + (uint64_t)(VT_PLANE >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < 3; ++ks) {
+                                const uint64_t o = (uint64_t)(ks * 2);
+                                ptx::umma_bf16(td, p_lo + o, v_hi + o, ID96, ks > 0 ? 1u : 0u);
+                                ptx::umma_bf16(td, p_hi + o, v_lo + o, ID96, 1u);
+                                ptx::umma_bf16(td, p_hi + o, v_hi + o, ID96, 1u);
+                            }
+                        }
+                        ptx::umma_commit(bar_at(smem, B_PVD_FULL));
+                        ++gv;
+                        issued = true;
+                    }
                 }
-                ptx::umma_commit(bar_at(smem, B_WO_EMPTY + so));
-                if (last_head) {
-                    ptx::umma_commit(bar_at(smem, B_OUT_FULL));
-                    if (g + 2 < NG) issue_qkv(g + 2);
-                    h = 0; ++it;
-                } else {
-                    ++h;
+                // ---- S = Q K^T : rows [hi | lo]: K-steps 0,1 = hi dims, 2,3 = lo dims
+                if (gk < NG) {
+                    if (mbar_test(bar_at(smem, B_QK_READY), gk & 1) && (gk == 0 || mbar_test(bar_at(smem, B_S_EMPTY), (gk - 1) & 1))) {
+                        ptx::tc_fence_after();
+                        TR(3, gk, true);
+                        const uint32_t td = tmem_base + T_S;
+                        ptx::umma_bf16(td, d_q + 4, d_k + 0, ID128, 0u);      // q_lo . k_hi
+                        ptx::umma_bf16(td, d_q + 6, d_k + 2, ID128, 1u);
+                        ptx::umma_bf16(td, d_q + 0, d_k + 4, ID128, 1u);      // q_hi . k_lo
+                        ptx::umma_bf16(td, d_q + 2, d_k + 6, ID128, 1u);
+                        ptx::umma_bf16(td, d_q + 0, d_k + 0, ID128, 1u);      // q_hi . k_hi
+                        ptx::umma_bf16(td, d_q + 2, d_k + 2, ID128, 1u);
+                        ptx::umma_commit(bar_at(smem, B_S_FULL));
+                        ++gk;
+                        issued = true;
+                    }
                 }
+                // ---- q | k | v of one head: Xn . [W_hi | W_lo]^T into T_QKV[gq & 1]
+                if (gq < NG) {
+                    const uint32_t s = gq & 1u, par = (gq >> 1) & 1u;
+                    if ((h_q != 0 || mbar_test(bar_at(smem, B_XN_FULL), it_q & 1)) && mbar_test(bar_at(smem, B_WQ_FULL + s), par) &&
+                        mbar_test(bar_at(smem, B_QKV_EMPTY + s), par ^ 1)) {
+                        ptx::tc_fence_after();
+                        TR(1, gq, true);
+                        const uint32_t td = tmem_base + T_QKV + 96u * s;
+                        const uint64_t w_hi = d_wq + (uint64_t)((s * WQ_STAGE) >> 4), w_lo = w_hi + (uint64_t)(12288 >> 4);
+                        const uint64_t x_hi = d_xn, x_lo = d_xn + (uint64_t)(16384 >> 4);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t o = (uint64_t)(ks * 2);
+                            ptx::umma_bf16(td, x_lo + o, w_hi + o, ID96, ks > 0 ? 1u : 0u);
+                            ptx::umma_bf16(td, x_hi + o, w_lo + o, ID96, 1u);
+                            ptx::umma_bf16(td, x_hi + o, w_hi + o, ID96, 1u);
+                        }
+                        ptx::umma_commit(bar_at(smem, B_WQ_EMPTY + s));
+                        ptx::umma_commit(bar_at(smem, B_QKV_FULL + s));
+                        if (++h_q == heads) {                     // last qkv GEMM of the tile: the operand buffer may be refilled
+                            ptx::umma_commit(bar_at(smem, B_XN_EMPTY));
+                            h_q = 0; ++it_q;
+                        }
+                        ++gq;
+                        issued = true;
+                    }
+                }
+                if (!issued) __nanosleep(40);          // idle pass: leave the issue slots of this scheduler to the compute warps
             }
         }
-    } else if (warp == 2 || warp == 3) {
-        // ===================== LayerNorm producers: x rows of the next tile -> registers -> XN =====================
-        const int t64 = (int)threadIdx.x - 64;          // 0..63
-        const int l16 = t64 & 15, rg = t64 >> 4;        // 16 lanes per row, 4 rows per pass, 32 passes
+    } else if (warp < 6) {
+        // ===================== LayerNorm producers (warps 2-5): next tile's x rows -> normalised in registers -> XN ============
+        const int t128 = (int)threadIdx.x - 64;         // 0..127
+        const int l16 = t128 & 15, rg = t128 >> 4;      // 16 lanes per row, 8 rows per pass, 16 passes
         const float4 gam = *reinterpret_cast<const float4*>(a.gamma + l16 * 4);
-        const uint32_t sb_ln = ptx::smem_u32(smem) + OFF_XN;
+        const uint32_t sb_ln = sb + OFF_XN;
+        // global row of tile row `row` of tile `tile`: one division per tile (first pixel column), the other two columns follow
+        auto tile_base = [&](int tile, int& b0, int& rem0) { const int pc0 = tile * FG; b0 = pc0 / a.pix; rem0 = pc0 - b0 * a.pix; };
+        auto row_addr = [&](int tile, int b0, int rem0, int row) -> int64_t {       // -1: padding row / beyond the last pixel column
+            const int tpx = (row * 205) >> 13;                                       // row / 40 for row < 128
+            const int tf = row - tpx * FL;
+            if (row >= FG * FL || tile * FG + tpx >= a.n_pc) return -1;
+            int rem = rem0 + tpx, b = b0;
+            if (rem >= a.pix) { rem -= a.pix; ++b; }
+            return ((int64_t)(b * FL + tf) * a.pix + rem) * FC;
+        };
+        // tile epilogue (also this group's job: it idles between two LayerNorms): OUT (+bias) + x -> F32 and split-bf16 rows.
+        // thread = TMEM lane = tile row out of the accumulator; a 4x4 transpose of 16-byte chunks inside every lane quad (two
+        // shuffle butterflies) turns that into "4 lanes = 64 contiguous bytes of one row" for the global loads / stores (the
+        // thread-per-row form touches 32 lines per instruction and was measured to stall every shared-memory store of the SM)
+        const int eq = warp & 3, er = eq * 32 + lane;                  // TMEM lane quarter / tile row of this thread
+        const int ec = lane & 3;                                        // 16-byte chunk of each 64-byte group this lane ends up with
+        auto epilogue = [&](int tile_e, uint32_t it_e) {
+            ptx::mbar_wait(bar_at(smem, B_OUT_FULL), it_e & 1);
+            ptx::tc_fence_after();
+            uint32_t u[4][16];
+#pragma unroll
+            for (int part = 0; part < 4; ++part) tmem_ld16(tmem_base + ((uint32_t)(eq * 32) << 16) + T_OUT + 16u * (uint32_t)part, u[part]);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            warp_arrive(bar_at(smem, B_OUT_EMPTY), lane);             // out(head 0) of the next tile may overwrite the accumulator
+            int64_t goff[4];                                            // element offsets of the 4 tile rows of this lane's quad
+            {
+                int b0, rem0;
+                tile_base(tile_e, b0, rem0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) goff[j] = row_addr(tile_e, b0, rem0, (er & ~3) + j);
+            }
+            const bool up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+#pragma unroll
+            for (int part = 0; part < 4; ++part) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[part][i]);
+                // stage 1 (lanes a, a^2): slot s <- (row (s&2)|(a&1), chunk (a&2)|(s&1));  stage 2 (lanes a, a^1): slot s <- (row s, chunk a)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float send = up2 ? v[4 * c + e] : v[4 * (c + 2) + e];
+                        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+                        if (up2) v[4 * c + e] = recv; else v[4 * (c + 2) + e] = recv;
+                    }
+#pragma unroll
+                for (int sp = 0; sp < 4; sp += 2)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float send = up1 ? v[4 * sp + e] : v[4 * (sp + 1) + e];
+                        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                        if (up1) v[4 * sp + e] = recv; else v[4 * (sp + 1) + e] = recv;
+                    }
+                const int col = part * 16 + ec * 4;
+                float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.out_bias) ob = __ldg(reinterpret_cast<const float4*>(a.out_bias + col));
+                float4 xres[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    xres[j] = goff[j] >= 0 ? *reinterpret_cast<const float4*>(a.x + goff[j] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (goff[j] >= 0) {
+                        const float4 t4 = make_float4(v[4 * j] + xres[j].x + ob.x, v[4 * j + 1] + xres[j].y + ob.y,
+                                                      v[4 * j + 2] + xres[j].z + ob.z, v[4 * j + 3] + xres[j].w + ob.w);
+                        if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + goff[j] + col) = t4;
+                        if (a.out_sb) store_sb4(a.out_sb, a.out_plane, goff[j] + col, t4);
+                    }
+                }
+            }
+            TR(23, it_e, t128 == 0);
+        };
         uint32_t it = 0;
+        int tile_prev = -1;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                float4 v[16];
+            float4 v[16];
+            int b0, rem0;
+            tile_base(tile, b0, rem0);
 #pragma unroll
-                for (int p = 0; p < 16; ++p) {
-                    const int row = (half * 16 + p) * 4 + rg;
-                    const int tpx = row / FL, tf = row - tpx * FL;
-                    const int pc = tile * FG + tpx;
-                    const bool ok = row < FG * FL && pc < a.n_pc;
-                    const int64_t grow = ok ? ((int64_t)(pc / a.pix) * FL + tf) * a.pix + (pc % a.pix) : 0;
-                    v[p] = ok ? *reinterpret_cast<const float4*>(a.x + grow * FC + l16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (half == 0) ptx::mbar_wait(bar_at(smem, B_XN_EMPTY), (it & 1) ^ 1);     // previous tile's qkv GEMMs are done with XN
+            for (int p = 0; p < 16; ++p) {
+                const int64_t off = row_addr(tile, b0, rem0, p * 8 + rg);
+                v[p] = off >= 0 ? *reinterpret_cast<const float4*>(a.x + off + l16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-                for (int p = 0; p < 16; ++p) {
-                    const int row = (half * 16 + p) * 4 + rg;
-                    float s = (v[p].x + v[p].y) + (v[p].z + v[p].w);
+            for (int p = 0; p < 16; ++p) {
+                float s = (v[p].x + v[p].y) + (v[p].z + v[p].w);
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    const float mean = s / (float)FC;
-                    const float d0 = v[p].x - mean, d1 = v[p].y - mean, d2 = v[p].z - mean, d3 = v[p].w - mean;
-                    float sq = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+                for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const float mean = s * (1.f / (float)FC);
+                const float d0 = v[p].x - mean, d1 = v[p].y - mean, d2 = v[p].z - mean, d3 = v[p].w - mean;
+                float sq = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                    const float rstd = 1.f / sqrtf(sq / (float)FC + a.eps);
-                    uint2 hv, lv;
-                    split2(d0 * rstd * gam.x, d1 * rstd * gam.y, hv.x, lv.x);
-                    split2(d2 * rstd * gam.z, d3 * rstd * gam.w, hv.y, lv.y);
-                    const uint32_t off = sb_ln + sw_off(row, l16 >> 1) + ((l16 & 1) << 3);
-                    sts64(off, hv.x, hv.y);
-                    sts64(off + 16384, lv.x, lv.y);
-                }
+                for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                const float rstd = rsqrtf(sq * (1.f / (float)FC) + a.eps);
+                v[p] = make_float4(d0 * rstd * gam.x, d1 * rstd * gam.y, d2 * rstd * gam.z, d3 * rstd * gam.w);
+            }
+            TR(24, it, t128 == 0);
+            ptx::mbar_wait(bar_at(smem, B_XN_EMPTY), (it & 1) ^ 1);     // previous tile's qkv GEMMs are done with XN
+            TR(25, it, t128 == 0);
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int row = p * 8 + rg;
+                uint2 hv, lv;
+                split2(v[p].x, v[p].y, hv.x, lv.x);
+                split2(v[p].z, v[p].w, hv.y, lv.y);
+                const uint32_t off = sb_ln + sw_off(row, l16 >> 1) + ((l16 & 1) << 3);
+                sts64(off, hv.x, hv.y);
+                sts64(off + 16384, lv.x, lv.y);
             }
             ptx::fence_proxy_async();
             warp_arrive(bar_at(smem, B_XN_FULL), lane);
+            TR(26, it, t128 == 0);
+            {   // next tile's rows towards L2 while this group is busy with the epilogue
+                const int tn = tile + (int)gridDim.x;
+                if (tn < n_tiles) {
+                    int bn, remn;
+                    tile_base(tn, bn, remn);
+                    const int64_t off = row_addr(tn, bn, remn, t128);
+                    if (off >= 0) { ptx::prefetch_l2(a.x + off); ptx::prefetch_l2(a.x + off + 32); }
+                }
+            }
+            if (tile_prev >= 0) epilogue(tile_prev, it - 1);           // the previous tile finishes ~3 heads after its last qkv GEMM
+            tile_prev = tile;
         }
+        if (tile_prev >= 0) epilogue(tile_prev, it - 1);
     } else {
-        // ===================== three compute warp-groups: A = warps 4-7, B = warps 8-11, C = warps 12-15 =====================
-        const int tc = (int)threadIdx.x - 128;          // 0..383
-        const int wg = tc >> 7;                          // 0: A (q, k), 1: B (v, O, epilogue), 2: C (softmax)
+        // ===================== three compute warp-groups: A = warps 6-9, B = warps 10-13, C = warps 14-17 =====================
+        const int tc = (int)threadIdx.x - 192;          // 0..383
+        const int wg = tc >> 7;                          // 0: A (q, k, QK), 1: B (v, O, out, epilogue), 2: C (softmax, PV)
+        const bool first = (tc & 127) == 0;              // the group's MMA-issuing thread
         const int q = warp & 3;                          // TMEM lane quarter
         const int r = q * 32 + lane;                     // tile row of this thread
         const int rpx = r / FL;                          // 0..3 (3 = pad rows)
@@ -483,12 +555,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
         const int pxhi_raw = (q * 32 + 31) / FL;
         const int pxhi = pxhi_raw < FG ? pxhi_raw : FG - 1;
         const bool straddle = pxhi != pxlo;              // warp-uniform
+        const bool use_hi = straddle && px != pxlo;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t sb = ptx::smem_u32(smem);
         const int dbg_ld = 3 * hid + heads * FL + hid;
+        auto grow_of = [&](int tile) -> int64_t {
+            const int pc = tile * FG + rpx;
+            return (row_real && pc < a.n_pc) ? ((int64_t)(pc / a.pix) * FL + fr) * a.pix + (pc % a.pix) : -1;
+        };
 
         if (wg == 0) {
-            // ---------- WG-A: q*scale, rotary(q), rotary(k) -> operand rows, head after head across tiles ----------
+            // ---------- WG-A: q*scale, rotary(q), rotary(k) -> operand rows; QK(g) ----------
             float rc[16], rs[16];                        // rotary table row of this thread's frame
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
@@ -499,29 +575,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
             }
             uint32_t g = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                int64_t my_grow = -1;
-                if (DBG) {
-                    const int pc = tile * FG + rpx;
-                    if (row_real && pc < a.n_pc) my_grow = ((int64_t)(pc / a.pix) * FL + fr) * a.pix + (pc % a.pix);
-                }
+                const int64_t my_grow = DBG ? grow_of(tile) : -1;
                 for (int h = 0; h < heads; ++h, ++g) {
-                    const uint32_t t_qkv = lane_base + T_QKV;
-                    TR(8, g, r == 0);
-                    ptx::mbar_wait(bar_at(smem, B_QKV_FULL), g & 1);
-                    TR(9, g, r == 0);
-                    if (g > 0) ptx::mbar_wait(bar_at(smem, B_S_FULL + ((g - 1) & 1)), ((g - 1) >> 1) & 1);   // QK(g-1) is done with Q / K
+                    const uint32_t s = g & 1u;
+                    const uint32_t t_qkv = lane_base + T_QKV + 96u * s;
+                    TR(8, g, first);
+                    ptx::mbar_wait(bar_at(smem, B_QKV_FULL + s), (g >> 1) & 1);
+                    TR(9, g, first);
+                    if (g > 0) ptx::mbar_wait(bar_at(smem, B_S_FULL), (g - 1) & 1);     // QK(g-1) is done with Q / K
                     ptx::tc_fence_after();
-                    TR(10, g, r == 0);
+                    TR(10, g, first);
 #pragma unroll
                     for (int part = 0; part < 4; ++part) {       // q dims 0-15, 16-31, k dims 0-15, 16-31
                         uint32_t u[16];
                         float v[16];
                         tmem_ld16(t_qkv + 16u * (uint32_t)part, u);
                         ptx::tmem_ld_wait();
-                        const float scale = part < 2 ? 0.17677669529663687f : 1.f;       // q * 32^-0.5 (reference :325); k unscaled
+                        // (q * 32^-0.5 of the reference, :325, is folded into the packed q rows of W_qkv on the host)
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float x0 = __uint_as_float(u[2 * i]) * scale, y0 = __uint_as_float(u[2 * i + 1]) * scale;
+                            const float x0 = __uint_as_float(u[2 * i]), y0 = __uint_as_float(u[2 * i + 1]);
                             const float cc = rc[8 * (part & 1) + i], sn = rs[8 * (part & 1) + i];
                             v[2 * i] = x0 * cc - y0 * sn;
                             v[2 * i + 1] = y0 * cc + x0 * sn;
@@ -539,50 +612,168 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                     __syncwarp();
                     if (lane == 0) {
                         ptx::mbar_arrive(bar_at(smem, B_QK_READY));
-                        ptx::mbar_arrive(bar_at(smem, B_QKV_EMPTY));
+                        ptx::mbar_arrive(bar_at(smem, B_QKV_EMPTY + s));
                     }
-                    TR(11, g, r == 0);
+                    TR(11, g, first);
                 }
             }
         } else if (wg == 2) {
-            // ---------- WG-C: softmax rows ----------
+            // ---------- WG-C: softmax rows; PV(g) ----------
+            constexpr float L2E = 1.4426950408889634f;
             uint32_t g = 0, it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                int64_t my_grow = -1;
-                if (DBG) {
-                    const int pc = tile * FG + rpx;
-                    if (row_real && pc < a.n_pc) my_grow = ((int64_t)(pc / a.pix) * FL + fr) * a.pix + (pc % a.pix);
-                }
+                const int64_t my_grow = DBG ? grow_of(tile) : -1;
                 for (int h = 0; h < heads; ++h, ++g) {
-                    TR(12, g, r == 0);
-                    ptx::mbar_wait(bar_at(smem, B_S_FULL + (g & 1)), (g >> 1) & 1);
+                    TR(12, g, first);
+                    ptx::mbar_wait(bar_at(smem, B_S_FULL), g & 1);
                     ptx::tc_fence_after();
-                    TR(13, g, r == 0);
-                    softmax_row<DBG>(a, smem, sb, lane_base + T_S + 128u * (g & 1u), r, px, pxlo, pxhi, straddle, fr, h, g, h == 0 ? it : 0u,
-                                     my_grow, dbg_ld, hid);
+                    TR(13, g, first);
+                    float sv[FL];
+                    {
+                        // this row's 40 scores (column block of its pixel): all loads in flight, one wait per batch
+                        const uint32_t t_s = lane_base + T_S;
+                        if (!straddle) {
+                            uint32_t u[FL / 8][8];
+#pragma unroll
+                            for (int c = 0; c < FL / 8; ++c) tmem_ld8(t_s + (uint32_t)(FL * pxlo + 8 * c), u[c]);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int c = 0; c < FL / 8; ++c)
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) sv[8 * c + j] = __uint_as_float(u[c][j]);
+                        } else {
+                            {
+                                uint32_t u0[3][8], u1[3][8];
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) {
+                                    tmem_ld8(t_s + (uint32_t)(FL * pxlo + 8 * c), u0[c]);
+                                    tmem_ld8(t_s + (uint32_t)(FL * pxhi + 8 * c), u1[c]);
+                                }
+                                ptx::tmem_ld_wait();
+#pragma unroll
+                                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) sv[8 * c + j] = __uint_as_float(use_hi ? u1[c][j] : u0[c][j]);
+                            }
+                            {
+                                uint32_t u0[2][8], u1[2][8];
+#pragma unroll
+                                for (int c = 0; c < 2; ++c) {
+                                    tmem_ld8(t_s + (uint32_t)(FL * pxlo + 24 + 8 * c), u0[c]);
+                                    tmem_ld8(t_s + (uint32_t)(FL * pxhi + 24 + 8 * c), u1[c]);
+                                }
+                                ptx::tmem_ld_wait();
+#pragma unroll
+                                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) sv[24 + 8 * c + j] = __uint_as_float(use_hi ? u1[c][j] : u0[c][j]);
+                            }
+                        }
+                    }
                     ptx::tc_fence_before();
+                    warp_arrive(bar_at(smem, B_S_EMPTY), lane);          // QK(g+1) may overwrite the scores
+                    if (a.pos_bias) {      // T5 relative-position bias row (h, frame): L1 / L2 resident
+                        const float4* bp = reinterpret_cast<const float4*>(a.pos_bias + ((int64_t)h * FL + fr) * FL);
+#pragma unroll
+                        for (int i = 0; i < FL / 4; ++i) {
+                            const float4 t4 = __ldg(bp + i);
+                            sv[4 * i] += t4.x; sv[4 * i + 1] += t4.y; sv[4 * i + 2] += t4.z; sv[4 * i + 3] += t4.w;
+                        }
+                    }
+                    float m0 = fmaxf(sv[0], sv[1]), m1 = fmaxf(sv[2], sv[3]), m2 = fmaxf(sv[4], sv[5]), m3 = fmaxf(sv[6], sv[7]);
+#pragma unroll
+                    for (int j = 8; j < FL; j += 4) {
+                        m0 = fmaxf(m0, sv[j]); m1 = fmaxf(m1, sv[j + 1]); m2 = fmaxf(m2, sv[j + 2]); m3 = fmaxf(m3, sv[j + 3]);
+                    }
+                    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    const float nb = -mx * L2E;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < FL; j += 4) {
+                        sv[j] = ex2(fmaf(sv[j], L2E, nb)); sv[j + 1] = ex2(fmaf(sv[j + 1], L2E, nb));
+                        sv[j + 2] = ex2(fmaf(sv[j + 2], L2E, nb)); sv[j + 3] = ex2(fmaf(sv[j + 3], L2E, nb));
+                        s0 += sv[j]; s1 += sv[j + 1]; s2 += sv[j + 2]; s3 += sv[j + 3];
+                    }
+                    // P stays un-normalised (exp(s - max) in (0, 1]); WG-B scales the PV result by 1 / sum instead (32 products
+                    // per row there instead of 40 here: this group is the slowest stage of the pipeline)
+                    const float inv = 1.f / ((s0 + s1) + (s2 + s3));
+                    if (DBG) {
+                        if (a.dbg && my_grow >= 0) {
+#pragma unroll
+                            for (int j = 0; j < FL; ++j) a.dbg[my_grow * dbg_ld + 3 * hid + h * FL + j] = sv[j] * inv;
+                        }
+                    }
+                    TR(14, g, first);
+                    // P is single-buffered: PV of the previous head must have read it
+                    if (g > 0) ptx::mbar_wait(bar_at(smem, B_PVD_FULL), (g - 1) & 1);
+                    TR(15, g, first);
+                    // slot g & 1 was last read for head g-2, before WG-B released the accumulator that PV(g-1) -- just seen complete --
+                    // had to wait for; WG-B sees this store through P_READY -> PV(g) -> PVD_FULL
+                    reinterpret_cast<float*>(smem + OFF_INV)[(g & 1u) * 128u + (uint32_t)r] = inv;
+#pragma unroll
+                    for (int c = 0; c < FL / 8; ++c) {
+                        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                        split2(sv[8 * c], sv[8 * c + 1], h0, l0);
+                        split2(sv[8 * c + 2], sv[8 * c + 3], h1, l1);
+                        split2(sv[8 * c + 4], sv[8 * c + 5], h2, l2);
+                        split2(sv[8 * c + 6], sv[8 * c + 7], h3, l3);
+                        sts128(sb + OFF_P + sw_off(r, c), h0, h1, h2, h3);
+                        sts128(sb + OFF_P + 16384 + sw_off(r, c), l0, l1, l2, l3);
+                    }
                     ptx::fence_proxy_async();
                     warp_arrive(bar_at(smem, B_P_READY), lane);
-                    TR(16, g, r == 0);
+                    TR(16, g, first);
                 }
             }
         } else {
-            // ---------- WG-B: v -> transposed compact operand; PV result -> O operand rows; tile epilogue ----------
+            // ---------- WG-B: v(g) -> transposed compact operand (one head ahead); PV(g-1) result -> O operand rows, out(g-1);
+            // ---------- tile epilogue ----------
             const int t128 = tc & 127;
             const int l16 = t128 & 15, rg = t128 >> 4;   // store mapping of the epilogue: 16 lanes per row, 8 rows per pass
-            uint32_t g = 0, it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                int64_t my_grow = -1;
-                if (DBG) {
-                    const int pc = tile * FG + rpx;
-                    if (row_real && pc < a.n_pc) my_grow = ((int64_t)(pc / a.pix) * FL + fr) * a.pix + (pc % a.pix);
-                }
-                for (int h = 0; h < heads; ++h, ++g) {
-                    const uint32_t t_qkv = lane_base + T_QKV;
-                    TR(17, g, r == 0);
-                    ptx::mbar_wait(bar_at(smem, B_QKV_FULL), g & 1);
-                    ptx::tc_fence_after();
-                    TR(18, g, r == 0);
+            int h_v = 0, tile_v = blockIdx.x;            // cursor of the v stage
+            int h_o = 0, tile_o = blockIdx.x;            // cursor of the O / out stage
+            int64_t grow_v = DBG ? grow_of(tile_v) : -1, grow_o = grow_v;
+            // v of head g -> B operand buffer g & 1 (last read by PV(g-2), whose completion this group has waited for)
+            auto do_v = [&](uint32_t g) {
+                const uint32_t s = g & 1u;
+                const uint32_t t_qkv = lane_base + T_QKV + 96u * s;
+                TR(17, g, first);
+                ptx::mbar_wait(bar_at(smem, B_QKV_FULL + s), (g >> 1) & 1);
+                ptx::tc_fence_after();
+                TR(18, g, first);
+                const uint32_t vt = sb + OFF_VT + s * VT_BUF;
+                if (VMN) {
+                    uint32_t u0[16], u1[16];
+                    tmem_ld16(t_qkv + 64u, u0);
+                    tmem_ld16(t_qkv + 80u, u1);
+                    ptx::tmem_ld_wait();
+                    if (row_real) {
+                        // row k = frame of the [position][column] tile; this row's 32 columns = 64 contiguous bytes
+                        const uint32_t base = vt + (uint32_t)((px >> 1) * VMN_ATOM + (fr >> 3) * 1024 + (fr & 7) * 128);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t* u = c < 2 ? u0 : u1;
+                            const int o = (c & 1) * 8;
+                            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                            split2(__uint_as_float(u[o]), __uint_as_float(u[o + 1]), h0, l0);
+                            split2(__uint_as_float(u[o + 2]), __uint_as_float(u[o + 3]), h1, l1);
+                            split2(__uint_as_float(u[o + 4]), __uint_as_float(u[o + 5]), h2, l2);
+                            split2(__uint_as_float(u[o + 6]), __uint_as_float(u[o + 7]), h3, l3);
+                            const uint32_t off = base + (uint32_t)(((((px & 1) << 2) + c) ^ (fr & 7)) << 4);
+                            sts128(off, h0, h1, h2, h3);
+                            sts128(off + VT_PLANE, l0, l1, l2, l3);
+                        }
+                        if (DBG) {
+                            if (a.dbg && grow_v >= 0) {
+#pragma unroll
+                                for (int dd = 0; dd < 16; ++dd) {
+                                    a.dbg[grow_v * dbg_ld + 2 * hid + h_v * 32 + dd] = __uint_as_float(u0[dd]);
+                                    a.dbg[grow_v * dbg_ld + 2 * hid + h_v * 32 + 16 + dd] = __uint_as_float(u1[dd]);
+                                }
+                            }
+                        }
+                    }
+                } else {
 #pragma unroll
                     for (int part = 0; part < 2; ++part) {
                         uint32_t u[16];
@@ -596,110 +787,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_temporal_fused_kernel(const 
                                 const bf16 hi = __float2bfloat16_rn(x0);
                                 const bf16 lo = __float2bfloat16_rn(x0 - __bfloat162float(hi));
                                 const int n = px * 32 + d;
-                                const uint32_t off = sb + OFF_VT + sw_off(n, fr >> 3) + (uint32_t)((fr & 7) * 2);
+                                const uint32_t off = vt + sw_off(n, fr >> 3) + (uint32_t)((fr & 7) * 2);
                                 sts16(off, *reinterpret_cast<const uint16_t*>(&hi));
                                 sts16(off + VT_PLANE, *reinterpret_cast<const uint16_t*>(&lo));
                             }
                             if (DBG) {
-                                if (a.dbg && my_grow >= 0) {
+                                if (a.dbg && grow_v >= 0) {
 #pragma unroll
-                                    for (int dd = 0; dd < 16; ++dd) a.dbg[my_grow * dbg_ld + 2 * hid + h * 32 + 16 * part + dd] = __uint_as_float(u[dd]);
+                                    for (int dd = 0; dd < 16; ++dd) a.dbg[grow_v * dbg_ld + 2 * hid + h_v * 32 + 16 * part + dd] = __uint_as_float(u[dd]);
                                 }
                             }
                         }
-                    }
-                    ptx::tc_fence_before();
-                    ptx::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        ptx::mbar_arrive(bar_at(smem, B_VT_READY));
-                        ptx::mbar_arrive(bar_at(smem, B_QKV_EMPTY));
-                    }
-                    // this row's 32 output columns -> O operand row
-                    TR(19, g, r == 0);
-                    ptx::mbar_wait(bar_at(smem, B_PVD_FULL), g & 1);
-                    ptx::tc_fence_after();
-                    TR(20, g, r == 0);
-                    {
-                        const bool use_hi = straddle && px != pxlo;
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            float v[16];
-#pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                uint32_t u0[8], u1[8];
-                                tmem_ld8(lane_base + T_PVD + (uint32_t)(32 * pxlo + 16 * half + 8 * c), u0);
-                                if (straddle) tmem_ld8(lane_base + T_PVD + (uint32_t)(32 * pxhi + 16 * half + 8 * c), u1);
-                                ptx::tmem_ld_wait();
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[8 * c + j] = __uint_as_float(use_hi ? u1[j] : u0[j]);
-                            }
-                            store_hilo_half(sb + OFF_O, r, half, v);
-                            if (DBG) {
-                                if (a.dbg && my_grow >= 0) {
-#pragma unroll
-                                    for (int i = 0; i < 16; ++i) a.dbg[my_grow * dbg_ld + 3 * hid + heads * FL + h * 32 + 16 * half + i] = v[i];
-                                }
-                            }
-                        }
-                    }
-                    ptx::tc_fence_before();
-                    ptx::fence_proxy_async();
-                    warp_arrive(bar_at(smem, B_O_READY), lane);
-                    TR(21, g, r == 0);
-                }
-
-                // ---------------- epilogue: OUT (+bias) + x -> global, coalesced through the P operand buffer ----------------
-                float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a.out_bias) ob = __ldg(reinterpret_cast<const float4*>(a.out_bias + l16 * 4));
-                ptx::mbar_wait(bar_at(smem, B_OUT_FULL), it & 1);       // implies PV of the last head is done with P
-                ptx::tc_fence_after();
-#pragma unroll
-                for (int part = 0; part < 4; ++part) {
-                    uint32_t u[16];
-                    tmem_ld16(lane_base + T_OUT + 16u * (uint32_t)part, u);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int lc = part * 4 + c;
-                        sts128(sb + OFF_P + (uint32_t)(r * 256 + ((lc ^ (r & 7)) << 4)), u[4 * c], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
                     }
                 }
                 ptx::tc_fence_before();
-                warp_arrive(bar_at(smem, B_OUT_EMPTY), lane);
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::mbar_arrive(bar_at(smem, B_VT_READY + s));
+                    ptx::mbar_arrive(bar_at(smem, B_QKV_EMPTY + s));
+                }
+                TR(19, g, first);
+                if (++h_v == heads) { h_v = 0; tile_v += gridDim.x; if (DBG) grow_v = grow_of(tile_v); }
+            };
+            do_v(0);
+            if (NG > 1) do_v(1);
+            // downstream first: O(gp) / out(gp) as soon as PV(gp) lands (PV(gp+1) waits for this group to drain the accumulator),
+            // then v two heads ahead while the softmax of the next head is still running
+            for (uint32_t gp = 0; gp < NG; ++gp) {
+                // ---- this row's 32 output columns of PV(gp) -> O operand row
+                ptx::mbar_wait(bar_at(smem, B_PVD_FULL), gp & 1);
+                ptx::tc_fence_after();
+                TR(20, gp, first);
+                float ov[32];
+                {
+                    uint32_t u0[4][8], u1[4][8];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        tmem_ld8(lane_base + T_PVD + (uint32_t)(32 * pxlo + 8 * c), u0[c]);
+                        if (straddle) tmem_ld8(lane_base + T_PVD + (uint32_t)(32 * pxhi + 8 * c), u1[c]);
+                    }
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    const float inv = reinterpret_cast<const float*>(smem + OFF_INV)[(gp & 1u) * 128u + (uint32_t)r];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) ov[8 * c + j] = __uint_as_float(use_hi ? u1[c][j] : u0[c][j]) * inv;
+                }
+                ptx::tc_fence_before();
+                warp_arrive(bar_at(smem, B_PVD_EMPTY), lane);            // PV(gp+1) may overwrite the accumulator
+                if (gp > 0) ptx::mbar_wait(bar_at(smem, B_O_FREE), (gp - 1) & 1);       // out(gp-1) has read the O operand
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    float4 xres[8];
+                    float v[16];
 #pragma unroll
-                    for (int p = 0; p < 8; ++p) {
-                        const int row = (half * 8 + p) * 8 + rg;
-                        const int tpx = row / FL, tf = row - tpx * FL;
-                        const int pc = tile * FG + tpx;
-                        const bool ok = row < FG * FL && pc < a.n_pc;
-                        const int64_t grow = ok ? ((int64_t)(pc / a.pix) * FL + tf) * a.pix + (pc % a.pix) : 0;
-                        xres[p] = ok ? *reinterpret_cast<const float4*>(a.x + grow * FC + l16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    for (int i = 0; i < 16; ++i) v[i] = ov[16 * half + i];
+                    store_hilo_half(sb + OFF_O, r, half, v);
+                }
+                if (DBG) {
+                    if (a.dbg && grow_o >= 0) {
 #pragma unroll
-                    for (int p = 0; p < 8; ++p) {
-                        const int row = (half * 8 + p) * 8 + rg;
-                        const int tpx = row / FL, tf = row - tpx * FL;
-                        const int pc = tile * FG + tpx;
-                        if (row < FG * FL && pc < a.n_pc) {
-                            const int64_t grow = ((int64_t)(pc / a.pix) * FL + tf) * a.pix + (pc % a.pix);
-                            float4 t4 = lds128f(sb + OFF_P + (uint32_t)(row * 256 + ((l16 ^ (row & 7)) << 4)));
-                            t4.x += xres[p].x + ob.x; t4.y += xres[p].y + ob.y; t4.z += xres[p].z + ob.z; t4.w += xres[p].w + ob.w;
-                            if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + grow * FC + l16 * 4) = t4;
-                            if (a.out_sb) store_sb4(a.out_sb, a.out_plane, grow * FC + l16 * 4, t4);
-                        }
+                        for (int i = 0; i < 32; ++i) a.dbg[grow_o * dbg_ld + 3 * hid + heads * FL + h_o * 32 + i] = ov[i];
                     }
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
-                // the staging tile overwrote P's zero pad (positions 40..47 = chunk 5 of both planes): restore it, then release P
-                sts128(sb + OFF_P + sw_off(r, 5), 0u, 0u, 0u, 0u);
-                sts128(sb + OFF_P + 16384 + sw_off(r, 5), 0u, 0u, 0u, 0u);
                 ptx::fence_proxy_async();
-                warp_arrive(bar_at(smem, B_STG_FREE), lane);
+                warp_arrive(bar_at(smem, B_O_READY), lane);
+                TR(21, gp, first);
+                if (gp + 2 < NG) do_v(gp + 2);
+                if (++h_o == heads) { h_o = 0; tile_o += gridDim.x; if (DBG) grow_o = grow_of(tile_o); }
             }
         }
     }
@@ -731,9 +887,12 @@ int lfdm_attn_temporal_fused(const float* x, const float* gamma, const void* wq_
     static bool attr_done[64] = {};
     static int sms[64] = {};
     if (dev < 0 || dev >= 64) return LFDM_E_UNSUPP;
+    static const bool vmn = (getenv("LFDM_ATTN_VT_KMAJOR") == nullptr);     // A/B switch: K-major transposed V^T operand
     if (!attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(attn_temporal_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_temporal_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(attn_temporal_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_temporal_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_temporal_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_temporal_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (sms[dev] <= 0) sms[dev] = 148;
@@ -749,9 +908,13 @@ int lfdm_attn_temporal_fused(const float* x, const float* gamma, const void* wq_
     if (trace_mode && debug) { a.trace = reinterpret_cast<long long*>(debug); a.dbg = nullptr; debug = nullptr; }
     a.heads = heads; a.n_pc = n_b * pixels; a.pix = pixels; a.n_tiles = (a.n_pc + FG - 1) / FG; a.eps = eps;
     const int grid = a.n_tiles < sms[dev] ? a.n_tiles : sms[dev];
-    if (debug)
-        LFDM_LAUNCH_PDL(attn_temporal_fused_kernel<true>, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a);
+    if (debug && vmn)
+        LFDM_LAUNCH_PDL((attn_temporal_fused_kernel<true, true>), dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a);
+    else if (debug)
+        LFDM_LAUNCH_PDL((attn_temporal_fused_kernel<true, false>), dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a);
+    else if (vmn)
+        LFDM_LAUNCH_PDL((attn_temporal_fused_kernel<false, true>), dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a);
     else
-        LFDM_LAUNCH_PDL(attn_temporal_fused_kernel<false>, dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a);
+        LFDM_LAUNCH_PDL((attn_temporal_fused_kernel<false, false>), dim3(grid), dim3(NTHREADS), (size_t)SMEM_BYTES, st, a);
     return 0;
 }

@@ -50,6 +50,14 @@ inline cudaError_t lfdm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 blo
         if (e__ != cudaSuccess) return (int)e__;              \
     } while (0)
 
+// The > 48 KiB dynamic-shared-memory opt-in (cudaFuncSetAttribute) is PER DEVICE: one flag per device ordinal, not per process.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    // -> true when the caller still has to run the one-time set-up for the current device
+    bool need() const { int d = 0; cudaGetDevice(&d); return d < 0 || d >= 64 || !done[d]; }
+    void mark() { int d = 0; cudaGetDevice(&d); if (d >= 0 && d < 64) done[d] = true; }
+};
+
 __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi)

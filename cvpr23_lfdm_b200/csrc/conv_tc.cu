@@ -684,18 +684,16 @@ template <int BN, int STAGES, bool WIDE>
 int launch(const TcArgs& a, cudaStream_t st) {
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BN * BK * 2;
     constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 8 * 4096 + 256 + 512;   // + 8 staging tiles + barriers + GN accumulators
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    static int num_sms = 0;
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
-    static int num_sms = 0;
-    if (!num_sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
+        once.mark();
     }
     int total = a.m_tiles * a.n_tiles;
     int grid = total < num_sms ? total : num_sms;

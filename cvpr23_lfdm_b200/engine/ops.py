@@ -253,7 +253,8 @@ def pack_fused_attention(qkv_w, out_w, heads):
     assert qkv_w.shape[1] == 64 and out_w.shape[0] == 64
     wq, wo = [], []
     for h in range(heads):
-        wh = torch.cat([qkv_w[h * 32:(h + 1) * 32], qkv_w[hid + h * 32:hid + (h + 1) * 32],
+        # q rows carry the softmax scale 32^-0.5 (reference :325 scales q after the projection; the kernel does not)
+        wh = torch.cat([qkv_w[h * 32:(h + 1) * 32] * (32 ** -0.5), qkv_w[hid + h * 32:hid + (h + 1) * 32],
                         qkv_w[2 * hid + h * 32:2 * hid + (h + 1) * 32]], 0)                   # (96, 64): q_h; k_h; v_h
         pl = split_planes(wh)                                                                  # (2, 96, 64)
         wq.append(torch.stack([_sw128_image(pl[0]), _sw128_image(pl[1])], 0))

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+rm -f gpurun_out/r02_parity_errors.jsonl
+timeout 1500 python -m pytest tests -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/t_all.log 2>&1; grep -E "passed|failed|^FAILED|^ERROR" gpurun_out/t_all.log | head -20
+timeout 700 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-700 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 200 python tools/eval_breakdown.py > gpurun_out/breakdown.md 2> gpurun_out/breakdown.err; head -3 gpurun_out/breakdown.md

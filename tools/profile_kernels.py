@@ -198,6 +198,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--noflush", action="store_true", help="keep the L2 warm between iterations (diagnostic only)")
     args = ap.parse_args()
     hbm, tf, src = peaks()
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
@@ -210,7 +211,8 @@ def main():
         torch.cuda.synchronize()
         ts = []
         for _ in range(args.iters):
-            flush.fill_(0.0)
+            if not args.noflush:
+                flush.fill_(0.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda._sleep(1_000_000)      # park the GPU ~0.5 ms: the host enqueues the launch ahead, no launch gap inside the interval
             e0.record()
