@@ -60,6 +60,7 @@ def _declare(l):
         "lfdm_attn_softmax_pre": [vp, vp, i64, vp, i64, i32, i32, i64, i64, i64, i64, vp, vp],
         "lfdm_attn_linear": [vp, vp, i64, vp, i64, i32, i32, vp],
         "lfdm_attn_temporal_fused": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp, vp],
+        "lfdm_attn_linear_fused": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp],
         "lfdm_small_linear": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "lfdm_sinusoidal": [vp, vp, vp, i32, i32, vp],
         "lfdm_ss_combine": [vp, vp, vp, vp, i32, i32, vp],
@@ -91,7 +92,7 @@ def _declare(l):
 
 
 EXPORTED = ["lfdm_conv", "lfdm_gn_stats", "lfdm_gn_apply", "lfdm_layernorm", "lfdm_attn_softmax", "lfdm_attn_softmax_pre",
-            "lfdm_attn_linear", "lfdm_attn_temporal_fused",
+            "lfdm_attn_linear", "lfdm_attn_temporal_fused", "lfdm_attn_linear_fused",
             "lfdm_small_linear", "lfdm_sinusoidal", "lfdm_ss_combine", "lfdm_sampler_x0", "lfdm_sampler_quantile",
             "lfdm_sampler_update", "lfdm_warp_blend_rows", "lfdm_warp_blend_image", "lfdm_to_rows", "lfdm_from_rows",
             "lfdm_im2col_small", "lfdm_pad_replicate_rows", "lfdm_avgpool2_rows", "lfdm_unet_heads", "lfdm_unet_heads_cfg", "lfdm_split_bf16", "lfdm_version",

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblfdm_b200.so")
-SOURCES = ["capi.cu", "conv_simt.cu", "conv_tc.cu", "norm.cu", "attention.cu", "attn_fused.cu", "sampler.cu", "warp.cu", "misc.cu", "motion.cu", "render.cu"]
+SOURCES = ["capi.cu", "conv_simt.cu", "conv_tc.cu", "norm.cu", "attention.cu", "attn_fused.cu", "attn_linear_fused.cu", "sampler.cu", "warp.cu", "misc.cu", "motion.cu", "render.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -275,6 +275,42 @@ def attn_temporal_fused(x, gamma, wq, wo, out_bias, cos, sin, pos_bias, out_f32,
     return rc
 
 
+LINATTN_MAXP = 4      # LFDM_LINATTN_MAXP of include/lfdm_b200.h
+
+
+def pack_fused_linear_attention(qkv_w, out_w):
+    """to_qkv weight (768, 64) and to_out weight (64, 256) of SpatialLinearAttention (8 heads x 32) -> operand images of
+    lfdm_attn_linear_fused: wk / wv (2 halves, 2 planes, 128 rows, 64) rows (head, d|e); wq (4 chunks, 2 planes, 64 rows, 64);
+    wout fp32 (64, 256)."""
+    hid = 256
+    qkv_w = qkv_w.detach().float().reshape(3 * hid, -1)
+    assert qkv_w.shape[1] == 64 and out_w.numel() == 64 * hid
+    wq, wk, wv = qkv_w[:hid], qkv_w[hid:2 * hid], qkv_w[2 * hid:]
+
+    def img(w, rows):            # (256, 64) -> (256 / rows, 2, rows, 64) swizzled split-bf16 images
+        out = []
+        for i in range(0, hid, rows):
+            pl = split_planes(w[i:i + rows])
+            out.append(torch.stack([_sw128_image(pl[0]), _sw128_image(pl[1])], 0))
+        return torch.stack(out, 0).contiguous()
+    return img(wk, 128), img(wv, 128), img(wq, 64), out_w.detach().float().reshape(64, hid).contiguous()
+
+
+def attn_linear_fused(x, gamma, packed, out_bias, out_f32, out_sb, frames, pos, eps, work=None):
+    """returns (rc, work): the C-ABI code (0, or L.E_UNSUPP when the geometry is not covered) and the work-space tensors
+    (partials, g_images) so that callers can keep them across calls"""
+    wk, wv, wq, wout = packed
+    if work is None or work[0].shape[0] != frames:
+        work = (torch.empty((frames, LINATTN_MAXP, 256, 34), device=x.device),
+                torch.empty((frames, 65536), dtype=torch.uint8, device=x.device))
+    rc = lib().lfdm_attn_linear_fused(ptr(x), ptr(gamma), ptr(wk), ptr(wv), ptr(wq), ptr(wout), ptr(out_bias), ptr(work[0]), ptr(work[1]),
+                                      ptr(out_f32), ptr(out_sb.t) if out_sb is not None else None,
+                                      out_sb.plane if out_sb is not None else 0, frames, pos, x.shape[1], 8, eps, stream())
+    if rc != L.E_UNSUPP:
+        check(rc, "lfdm_attn_linear_fused")
+    return rc, work
+
+
 def small_linear(x, w, b, y, act_in=0, act_out=0):
     rows, k = x.shape
     n = w.shape[0]

@@ -24,6 +24,9 @@ FUSE_ROTARY = os.environ.get("LFDM_FUSED_ROTARY") is not None
 # LFDM_FUSED_ATTN=0: compose the temporal-attention block from layernorm / qkv conv / attention core / out conv instead
 # of the single tcgen05 kernel lfdm_attn_temporal_fused (C = 64, 40 frames) -- A/B switch and cross-check.
 FUSED_ATTN = os.environ.get("LFDM_FUSED_ATTN", "1") == "1"
+# LFDM_FUSED_LINATTN=0: same switch for the spatial linear-attention block (lfdm_attn_linear_fused: C = 64, 8 heads,
+# positions per frame a multiple of 128).
+FUSED_LINATTN = os.environ.get("LFDM_FUSED_LINATTN", "1") == "1"
 
 
 def _rel_pos_bucket(n, num_buckets=32, max_distance=32):
@@ -58,7 +61,7 @@ class _Resnet:
 
 
 class _Attn:
-    def __init__(self, ln, qkv_w, out_w, out_b, heads, name):
+    def __init__(self, ln, qkv_w, out_w, out_b, heads, name, linear=False):
         self.gamma = ln.gamma.detach().float().reshape(-1).contiguous()
         self.eps = ln.eps
         c = self.gamma.numel()
@@ -68,8 +71,13 @@ class _Attn:
         self.hid = qkv_w.shape[0] // 3
         self.out_bias = out_b.detach().float().contiguous() if out_b is not None else None
         self.fused = None          # (wq, wo) operand images of the fused temporal block (C == 64)
+        self.fused_lin = None      # operand images of the fused linear-attention block (C == 64, 8 heads)
         if c == 64 and qkv_w.shape[0] == 3 * heads * 32:
-            self.fused = ops.pack_fused_attention(qkv_w, out_w, heads)
+            if linear:
+                if heads == 8:
+                    self.fused_lin = ops.pack_fused_linear_attention(qkv_w, out_w)
+            else:
+                self.fused = ops.pack_fused_attention(qkv_w, out_w, heads)
 
 
 class UnetEngine:
@@ -106,7 +114,7 @@ class UnetEngine:
         def l_attn(res_mod, name):      # Residual(PreNorm(SpatialLinearAttention))
             pre = res_mod.fn
             att = pre.fn
-            return _Attn(pre.norm, att.to_qkv.weight, att.to_out.weight, att.to_out.bias, att.heads, name)
+            return _Attn(pre.norm, att.to_qkv.weight, att.to_out.weight, att.to_out.bias, att.heads, name, linear=True)
 
         self.init_tattn = t_attn(unet.init_temporal_attn, "init_temporal_attn")
         # ---- time / cond MLPs
@@ -305,6 +313,12 @@ class UnetEngine:
 
     def _linear(self, at, x_f32, b, f, h, w):
         p = h * w
+        if FUSED_LINATTN and at.fused_lin is not None and p % 128 == 0:
+            m, c = x_f32.shape
+            out = f32(m, c, self.dev)
+            rc, _ = ops.attn_linear_fused(x_f32, at.gamma, at.fused_lin, at.out_bias, out, None, b * f, p, at.eps)
+            if rc == 0:
+                return out, None
         core = lambda qkv, o: ops.attn_linear(qkv, o, None, b * f, p, at.heads)
         return self._attn_common(at, x_f32, b * f, h, w, core, False)
 

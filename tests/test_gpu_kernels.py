@@ -356,6 +356,51 @@ def test_temporal_attention_block_fused(b, p, heads, with_bias):
     assert torch.equal(out2, out)
 
 
+def _linear_block_reference(x_rows, gamma, wqkv, wout, out_bias, frames, pos, heads=8, eps=1e-5):
+    """float64 restatement of Residual(PreNorm(SpatialLinearAttention)) (reference :132-138,170-190,240-265) on rows
+    [frame * pos + p][c]"""
+    hid = heads * 32
+    x = x_rows.double()
+    var = x.var(dim=1, unbiased=False, keepdim=True)
+    xn = (x - x.mean(1, keepdim=True)) / (var + eps).sqrt() * gamma.double()
+    qkv = (xn @ wqkv.double().t()).reshape(frames, pos, 3, heads, 32)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]              # (frames, pos, heads, 32)
+    q = q.softmax(dim=-1) * 32 ** -0.5                              # over d
+    k = k.softmax(dim=1)                                             # over the positions of the frame
+    ctx = torch.einsum("fnhd,fnhe->fhde", k, v)
+    o = torch.einsum("fhde,fnhd->fnhe", ctx, q).reshape(frames * pos, hid)
+    out = o @ wout.double().t() + out_bias.double() + x
+    return out.float()
+
+
+@pytest.mark.parametrize("frames,pos,wscale", [(3, 128, 1.0), (5, 256, 1.0), (2, 1024, 1.0), (40, 1024, 1.0), (7, 512, 6.0)])
+def test_linear_attention_block_fused(frames, pos, wscale):
+    """lfdm_attn_linear_fused (context partials -> merge -> apply, all GEMM stages on tcgen05) against a float64 restatement:
+    one / several tiles per frame, frames cut into segments across CTAs (40 x 1024: 640 tiles of 64 rows over 148 CTAs), and
+    large logits (wscale 6: the running maximum of a row grows by more than 2^8 between tiles -> accumulator re-basing)."""
+    from cvpr23_lfdm_b200.engine import ops
+    from cvpr23_lfdm_b200._lib import SB
+    g = torch.Generator().manual_seed(900 + frames + pos)
+    c, hid = 64, 256
+    m = frames * pos
+    x = torch.randn(m, c, generator=g) * 1.5 + 0.3
+    gamma = torch.randn(c, generator=g)
+    wqkv = torch.randn(3 * hid, c, generator=g) / 8 * wscale
+    wout = torch.randn(c, hid, generator=g) / 16
+    ob = torch.randn(c, generator=g)
+    ref = _linear_block_reference(x, gamma, wqkv, wout, ob, frames, pos)
+    packed = ops.pack_fused_linear_attention(wqkv.to(dev()), wout.to(dev()))
+    out, out_sb = torch.empty(m, c, device=dev()), SB(m, c, dev())
+    rc, work = ops.attn_linear_fused(x.to(dev()), gamma.to(dev()), packed, ob.to(dev()), out, out_sb, frames, pos, 1e-5)
+    assert rc == 0
+    torch.cuda.synchronize()
+    close(out, ref, "fused linear block: out f32")
+    close(out_sb.float(), ref, "fused linear block: out sb")
+    out2 = torch.empty(m, c, device=dev())
+    rc, _ = ops.attn_linear_fused(x.to(dev()), gamma.to(dev()), packed, ob.to(dev()), out2, None, frames, pos, 1e-5, work=work)
+    assert rc == 0 and torch.equal(out2, out)
+
+
 @pytest.mark.parametrize("f", [17, 24, 33, 39])
 def test_attn_temporal_ragged_lengths(f):
     """rotary + bias on frame counts that leave partial 16-row query tiles / odd bias rows (ldmatrix kernel, 17 <= L <= 40)"""

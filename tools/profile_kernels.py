@@ -126,6 +126,38 @@ def cases():
     c["tblock_fused_16"] = tblock(True, 16)
     c["tblock_unfused_16"] = tblock(False, 16)
 
+    def lblock(fused, hw=32):
+        def mk():
+            p, ch = hw * hw, 64
+            m = B * F * p
+            x = torch.randn(m, ch, device=dev)
+            gamma = torch.randn(ch, device=dev)
+            wqkv, wout = torch.randn(768, ch, 1, 1, device=dev) / 8, torch.randn(ch, 256, 1, 1, device=dev) / 16
+            ob = torch.randn(ch, device=dev)
+            out = torch.empty(m, ch, device=dev)
+            # algorithmic work: LN + to_qkv + (context + apply) + to_out; bytes: x read, out written
+            flops = 2.0 * m * ch * 768 + 4.0 * B * F * 8 * 32 * 32 * p + 2.0 * m * 256 * ch
+            byt = m * ch * 4 * 2
+            if fused:
+                packed = ops.pack_fused_linear_attention(wqkv, wout)
+                work = [None]
+
+                def run():
+                    _, work[0] = ops.attn_linear_fused(x, gamma, packed, ob, out, None, B * F, p, 1e-5, work=work[0])
+                return run, flops, byt, lambda: "tcgen05 fused linear block (3 launches, split-bf16 x3)"
+            lq, lo = ConvLayer(wqkv, None), ConvLayer(wout, ob)
+            n_sb, qkv, o = SB(m, ch, dev), torch.empty(m, 768, device=dev), SB(m, 256, dev)
+
+            def run():
+                ops.layernorm(x, gamma, out_sb=n_sb)
+                lq([n_sb], B * F, hw, hw, out_f32=qkv)
+                ops.attn_linear(qkv, o, None, B * F, p, 8)
+                lo([o], B * F, hw, hw, out_f32=out, residual=x)
+            return run, flops, byt, lambda: "4 kernels: layernorm + tcgen05 qkv + mma.sync core + tcgen05 out"
+        return mk
+    c["lblock_fused_32"] = lblock(True)
+    c["lblock_unfused_32"] = lblock(False)
+
     def attn_l():
         p, heads = 1024, 8
         m = B * F * p
