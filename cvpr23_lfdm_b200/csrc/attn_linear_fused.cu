@@ -16,9 +16,9 @@
 //        to shared memory as K-major split-bf16 operands and ctx[hd][he] += P^T V^T^T accumulates in TMEM (4 heads per
 //        128x128 accumulator; only the 4 diagonal 32x32 blocks are read).  At the end of a frame segment every thread writes
 //        its row (32 context values, maximum, denominator) to the partials buffer.
-//   2. linattn_combine_kernel (one small block per frame): merges the <= LFDM_LINATTN_MAXP partials of a frame, folds the
-//        q scale and 1 / denominator, and multiplies by W_out:  G[hd][c] = sum_e ctx[hd][e] W_out[c][h*32 + e], written as
-//        the split-bf16 B-operand image of launch 3.
+//   2. linattn_combine_kernel (one small block per (frame, 2-head chunk)): merges the <= LFDM_LINATTN_MAXP partials of a
+//        frame, folds the q scale and 1 / denominator, and multiplies by W_out:  G[hd][c] = sum_e ctx[hd][e] W_out[c][h*32 + e],
+//        written as the split-bf16 B-operand image of launch 3.
 //   3. linattn_apply_kernel (persistent, 128-row tiles): Q = Xn W_q^T in 64-column chunks (2 heads) through a 4-deep TMEM ring,
 //        softmax over d per (row, head) in registers, Qs -> split-bf16 A operand, OUT[128x64] += Qs_chunk G_chunk, epilogue
 //        OUT + bias + x -> F32 (and optional split-bf16) rows, coalesced by the quad transpose of attn_fused.cu.
@@ -389,65 +389,80 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_ctx_kernel(const __grid_c
 // ============================================================================================================================
 // launch 2: merge the partials of a frame, G = (scale * ctx / Z) W_out^T, as the B-operand image of launch 3
 // ============================================================================================================================
+// grid (4 chunks, frames): block (j, frame) merges the 64 rows (2 heads) of chunk j and writes its 16 KiB operand image
 __global__ void __launch_bounds__(256) linattn_combine_kernel(const __grid_constant__ LinArgs a, int tpc1, int tpf1) {
-    __shared__ float ctx[HID][33];
+    __shared__ float ctx[64][33];                   // rows (hh, d) of the chunk's 2 heads x 32 e, scaled
+    __shared__ float gsm[64][65];                   // G^T[c][hd] of the chunk
     pdl_trigger();
     pdl_wait();
-    const int frame = blockIdx.x;
-    const int t = threadIdx.x;                      // row (head, d)
+    const int j = blockIdx.x, frame = blockIdx.y;
+    const int t = threadIdx.x;
     const int c0 = (frame * tpf1) / tpc1, c1 = ((frame + 1) * tpf1 - 1) / tpc1;
     const int nparts = c1 - c0 + 1;
     {
-        const float* base = a.part + ((int64_t)frame * MAXP * HID + t) * PART_LD;
+        // thread (row = t / 4, e-octet = t % 4)
+        const int row = t >> 2, e0 = (t & 3) * 8;
+        const float* base = a.part + ((int64_t)frame * MAXP * HID + j * 64 + row) * PART_LD;
         float m = -INFINITY;
         for (int p = 0; p < nparts; ++p) m = fmaxf(m, base[(int64_t)p * HID * PART_LD + 32]);
-        float z = 0.f, acc[32];
+        float z = 0.f, acc[8];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
         for (int p = 0; p < nparts; ++p) {
-            const float* row = base + (int64_t)p * HID * PART_LD;
-            const float sc = exp2f(row[32] - m);
-            z += sc * row[33];
+            const float* rowp = base + (int64_t)p * HID * PART_LD;
+            const float sc = exp2f(rowp[32] - m);
+            z += sc * rowp[33];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) acc[e] += sc * row[e];
+            for (int e = 0; e < 8; e += 2) {
+                const float2 v2 = *reinterpret_cast<const float2*>(rowp + e0 + e);
+                acc[e] += sc * v2.x; acc[e + 1] += sc * v2.y;
+            }
         }
         const float f = 0.17677669529663687f / z;       // q * 32^-0.5 (reference :258) folded here
 #pragma unroll
-        for (int e = 0; e < 32; ++e) ctx[t][e] = acc[e] * f;
+        for (int e = 0; e < 8; ++e) ctx[row][e0 + e] = acc[e] * f;
     }
     __syncthreads();
-    // thread (chunk j = t / 64, output channel c = t % 64): row c of chunk j = G[hd = 64 j .. 64 j + 63][c]
-    const int j = t >> 6, c = t & 63;
-    float gv[64];
+    {
+        // thread (c = t % 64, d-octet = t / 64): G[hd = hh * 32 + d][c] = sum_e ctx[hd][e] W_out[c][(2 j + hh) * 32 + e]
+        const int c = t & 63, dq = t >> 6;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-        const int h = 2 * j + hh;
-        float w[32];
+        for (int hh = 0; hh < 2; ++hh) {
+            float w[32];
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(a.wout + (int64_t)c * HID + h * 32 + e);
-            w[e] = w4.x; w[e + 1] = w4.y; w[e + 2] = w4.z; w[e + 3] = w4.w;
-        }
+            for (int e = 0; e < 32; e += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(a.wout + (int64_t)c * HID + (2 * j + hh) * 32 + e);
+                w[e] = w4.x; w[e + 1] = w4.y; w[e + 2] = w4.z; w[e + 3] = w4.w;
+            }
 #pragma unroll
-        for (int d = 0; d < 32; ++d) {
-            const float* cr = ctx[h * 32 + d];
-            float s = 0.f;
+            for (int dd = 0; dd < 8; ++dd) {
+                const int hd = hh * 32 + dq * 8 + dd;
+                const float* cr = ctx[hd];
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) s = fmaf(cr[e], w[e], s);
-            gv[hh * 32 + d] = s;
+                for (int e = 0; e < 32; e += 2) { s0 = fmaf(cr[e], w[e], s0); s1 = fmaf(cr[e + 1], w[e + 1], s1); }
+                gsm[c][hd] = s0 + s1;
+            }
         }
     }
-    uint8_t* dst = a.gimg + ((int64_t)frame * 4 + j) * 16384;
+    __syncthreads();
+    {
+        // thread (row c = t / 4, 16-element quarter = t % 4): two 16-byte chunks of the hi and of the lo plane
+        const int c = t >> 2, qd = t & 3;
+        uint8_t* dst = a.gimg + ((int64_t)frame * 4 + j) * 16384;
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-        split2(gv[8 * ch], gv[8 * ch + 1], h0, l0);
-        split2(gv[8 * ch + 2], gv[8 * ch + 3], h1, l1);
-        split2(gv[8 * ch + 4], gv[8 * ch + 5], h2, l2);
-        split2(gv[8 * ch + 6], gv[8 * ch + 7], h3, l3);
-        const uint32_t off = sw_off(c, ch);
-        *reinterpret_cast<uint4*>(dst + off) = make_uint4(h0, h1, h2, h3);
-        *reinterpret_cast<uint4*>(dst + 8192 + off) = make_uint4(l0, l1, l2, l3);
+        for (int cc = 0; cc < 2; ++cc) {
+            const int ch = qd * 2 + cc;
+            const float* gv = &gsm[c][8 * ch];
+            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+            split2(gv[0], gv[1], h0, l0);
+            split2(gv[2], gv[3], h1, l1);
+            split2(gv[4], gv[5], h2, l2);
+            split2(gv[6], gv[7], h3, l3);
+            const uint32_t off = sw_off(c, ch);
+            *reinterpret_cast<uint4*>(dst + off) = make_uint4(h0, h1, h2, h3);
+            *reinterpret_cast<uint4*>(dst + 8192 + off) = make_uint4(l0, l1, l2, l3);
+        }
     }
 }
 
@@ -751,7 +766,7 @@ int lfdm_attn_linear_fused(const float* x, const float* gamma, const void* wk_pa
     a.tiles = tiles1; a.tpc = tpc1; a.tpf = tpf1;
     LFDM_LAUNCH_PDL(linattn_ctx_kernel, dim3(grid1), dim3(NTHREADS), (size_t)l1::SMEM_BYTES, st, a);
     // ---- launch 2
-    LFDM_LAUNCH_PDL(linattn_combine_kernel, dim3(frames), dim3(256), (size_t)0, st, a, tpc1, tpf1);
+    LFDM_LAUNCH_PDL(linattn_combine_kernel, dim3(4, frames), dim3(256), (size_t)0, st, a, tpc1, tpf1);
     // ---- launch 3: 128-row tiles, round-robin
     const int tiles3 = frames * (pos / 128);
     a.tiles = tiles3; a.tpc = 0; a.tpf = pos / 128;
