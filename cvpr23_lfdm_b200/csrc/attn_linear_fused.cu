@@ -38,7 +38,6 @@ constexpr int HID = 256;             // heads * 32
 constexpr int MAXP = LFDM_LINATTN_MAXP;
 constexpr int PART_LD = 34;          // floats per partial row: 32 context values, maximum (log2 domain), denominator
 constexpr int NTHREADS = 448;        // 14 warps
-constexpr float L2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.f;       // log2 units: rows are re-based only when their maximum grows by > 2^8
 
 struct LinArgs {
@@ -280,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_ctx_kernel(const __grid_c
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) kv[8 * c + j] = __uint_as_float(u[c][j]) * L2E;
+                        for (int j = 0; j < 8; ++j) kv[8 * c + j] = __uint_as_float(u[c][j]);       // log2 domain: W_k carries log2(e) (host packer)
                 }
                 ptx::tc_fence_before();
                 warp_arrive(bar_at(bars, B_KT_EMPTY + hf), lane);
@@ -687,7 +686,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_apply_kernel(const __grid
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) qv[8 * c + i] = __uint_as_float(u[c][i]) * L2E;
+                    for (int i = 0; i < 8; ++i) qv[8 * c + i] = __uint_as_float(u[c][i]);       // log2 domain: W_q carries log2(e) (host packer)
             }
             ptx::tc_fence_before();
             warp_arrive(bar_at(bars, B_Q_EMPTY + j), lane);

@@ -285,7 +285,9 @@ def pack_fused_linear_attention(qkv_w, out_w):
     hid = 256
     qkv_w = qkv_w.detach().float().reshape(3 * hid, -1)
     assert qkv_w.shape[1] == 64 and out_w.numel() == 64 * hid
-    wq, wk, wv = qkv_w[:hid], qkv_w[hid:2 * hid], qkv_w[2 * hid:]
+    # q and k only ever enter exp(): their projections carry log2(e) so that the kernels use ex2 without a multiply
+    l2e = 1.4426950408889634
+    wq, wk, wv = qkv_w[:hid] * l2e, qkv_w[hid:2 * hid] * l2e, qkv_w[2 * hid:]
 
     def img(w, rows):            # (256, 64) -> (256 / rows, 2, rows, 64) swizzled split-bf16 images
         out = []
