@@ -134,6 +134,12 @@ def build_model(cfg_name, sampling_steps=None):
     import cvpr23_lfdm_b200 as P
     cfg = CONFIGS[cfg_name]
     torch.manual_seed(1234)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):       # the reference-shaped constructor prints ("using ddim samping ..."): stdout is ONE JSON line
+        return _build(P, cfg, cfg_name, sampling_steps)
+
+
+def _build(P, cfg, cfg_name, sampling_steps):
     return P.FlowDiffusion(is_train=False, sampling_timesteps=sampling_steps or cfg["steps"], img_size=cfg["latent"],
                            num_frames=FRAMES, timesteps=1000, config_pth=os.path.join(ROOT, "config", cfg["yaml"]),
                            pretrained_pth="", **cfg["unet_kw"])

@@ -60,7 +60,7 @@ def _declare(l):
         "lfdm_attn_softmax_pre": [vp, vp, i64, vp, i64, i32, i32, i64, i64, i64, i64, vp, vp],
         "lfdm_attn_linear": [vp, vp, i64, vp, i64, i32, i32, vp],
         "lfdm_attn_temporal_fused": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp, vp],
-        "lfdm_attn_linear_fused": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp],
+        "lfdm_attn_linear_fused": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp],
         "lfdm_small_linear": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "lfdm_sinusoidal": [vp, vp, vp, i32, i32, vp],
         "lfdm_ss_combine": [vp, vp, vp, vp, i32, i32, vp],

@@ -19,7 +19,8 @@
 //   2. linattn_combine_kernel (one small block per (frame, 2-head chunk)): merges the <= LFDM_LINATTN_MAXP partials of a
 //        frame, folds the q scale and 1 / denominator, and multiplies by W_out:  G[hd][c] = sum_e ctx[hd][e] W_out[c][h*32 + e],
 //        written as the split-bf16 B-operand image of launch 3.
-//   3. linattn_apply_kernel (persistent, 128-row tiles): Q = Xn W_q^T in 64-column chunks (2 heads) through a 4-deep TMEM ring,
+//   3. linattn_apply_kernel (persistent, 128-row tiles; Xn comes back as the operand images launch 1 stored -- one 32 KiB bulk
+//        copy per tile instead of a second LayerNorm, which was this kernel's critical path): Q = Xn W_q^T in 64-column chunks (2 heads) through a 4-deep TMEM ring,
 //        softmax over d per (row, head) in registers, Qs -> split-bf16 A operand, OUT[128x64] += Qs_chunk G_chunk, epilogue
 //        OUT + bias + x -> F32 (and optional split-bf16) rows, coalesced by the quad transpose of attn_fused.cu.
 // Both persistent kernels use the role layout measured on the temporal block (attn_fused.cu): one POLLING issuer thread per
@@ -37,7 +38,8 @@ constexpr int HEADS = 8;
 constexpr int HID = 256;             // heads * 32
 constexpr int MAXP = LFDM_LINATTN_MAXP;
 constexpr int PART_LD = 34;          // floats per partial row: 32 context values, maximum (log2 domain), denominator
-constexpr int NTHREADS = 448;        // 14 warps
+constexpr int NTHREADS1 = 576;       // launch 1: 18 warps
+constexpr int NTHREADS = 448;        // launch 3: 14 warps
 constexpr float RESCALE_THRESHOLD = 8.f;       // log2 units: rows are re-based only when their maximum grows by > 2^8
 
 struct LinArgs {
@@ -50,6 +52,7 @@ struct LinArgs {
     const float* out_bias;       // [64] or null
     float* part;                 // [frames][MAXP][256][PART_LD]
     uint8_t* gimg;               // [frames][4 chunks][2 planes][64 rows x 128 B]  G^T operand images
+    uint8_t* ximg;               // [rows / 128][2 planes][128 rows x 128 B]       LayerNorm(x) operand images (written by launch 1)
     float* out_f32;
     bf16* out_sb;
     int64_t out_plane;
@@ -106,10 +109,11 @@ constexpr uint32_t T_KT = 0;         // 2 halves x 64 columns
 constexpr uint32_t T_VT = 128;       // 2 halves x 64
 constexpr uint32_t T_CTX = 256;      // 2 halves x 128
 enum { B_W_FULL = 0, B_XN_FULL = 1 /* 2 */, B_XN_EMPTY = 3 /* 2 */, B_KT_FULL = 5 /* 2 */, B_KT_EMPTY = 7 /* 2 */, B_VT_FULL = 9 /* 2 */,
-       B_VT_EMPTY = 11 /* 2 */, B_P_READY = 13, B_P_FREE = 14, B_V_READY = 15, B_V_FREE = 16, B_CTX_DONE = 17 /* 2 */, B_CTX_EMPTY = 19 /* 2 */ };
+       B_VT_EMPTY = 11 /* 2 */, B_P_READY = 13, B_V_READY = 15, B_V_FREE = 16, B_CTX_DONE = 17 /* 2 */, B_CTX_EMPTY = 19 /* 2 */,
+       B_P_FREE = 21 /* 2: [h] = the operand buffer is free for the group of half h (a parity wait must see EVERY phase of its barrier) */ };
 }  // namespace l1
 
-__global__ void __launch_bounds__(NTHREADS, 1) linattn_ctx_kernel(const __grid_constant__ LinArgs a) {
+__global__ void __launch_bounds__(NTHREADS1, 1) linattn_ctx_kernel(const __grid_constant__ LinArgs a) {
     using namespace l1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -134,6 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_ctx_kernel(const __grid_c
         }
         ptx::mbar_init(bar_at(bars, B_P_READY), 4);
         ptx::mbar_init(bar_at(bars, B_P_FREE), 1);
+        ptx::mbar_init(bar_at(bars, B_P_FREE + 1), 1);
         ptx::mbar_init(bar_at(bars, B_V_READY), 4);
         ptx::mbar_init(bar_at(bars, B_V_FREE), 1);
         ptx::fence_barrier_init();
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_ctx_kernel(const __grid_c
                             ptx::umma_bf16(td, p_hi + o, v_lo + o, ID128, 1u);
                             ptx::umma_bf16(td, p_hi + o, v_hi + o, ID128, 1u);
                         }
-                        ptx::umma_commit(bar_at(bars, B_P_FREE));
+                        ptx::umma_commit(bar_at(bars, B_P_FREE + (hf ^ 1u)));       // the next writer of P^T is the other half's group
                         ptx::umma_commit(bar_at(bars, B_V_FREE));
                         ptx::umma_commit(bar_at(bars, B_CTX_DONE + hf));
                         ++gc;
@@ -252,52 +257,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_ctx_kernel(const __grid_c
             ln_store<8, 8>(v, sb + OFF_XN + xb * 16384, 8192, rg, l16);
             ptx::fence_proxy_async();
             warp_arrive(bar_at(bars, B_XN_FULL + xb), lane);
+            // the same operand image goes to global memory: launch 3 bulk-copies it instead of normalising the rows again
+            {
+                const int tg = t_begin + tl;
+                uint8_t* img = a.ximg + (size_t)(tg >> 1) * 32768 + (size_t)(tg & 1) * 8192;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const int row = p * 8 + rg;
+                    uint2 hv, lv;
+                    split2(v[p].x, v[p].y, hv.x, lv.x);
+                    split2(v[p].z, v[p].w, hv.y, lv.y);
+                    const uint32_t off = sw_off(row, l16 >> 1) + ((l16 & 1) << 3);
+                    *reinterpret_cast<uint2*>(img + off) = hv;
+                    *reinterpret_cast<uint2*>(img + 16384 + off) = lv;
+                }
+            }
         }
     } else {
-        // ===================== WG-K (warps 6-9): rows (head, d) of K^T;  WG-V (warps 10-13): rows (head, e) of V^T =============
+        // ===================== WG-K0 / WG-K1 (warps 6-9 / 10-13): rows (head, d) of K^T of half 0 / 1; WG-V (warps 14-17) ======
         const int tc = (int)threadIdx.x - 192;
         const int wg = tc >> 7;
         const int q = warp & 3;
         const int r = q * 32 + lane;                     // operand row = TMEM lane: (head % 4) * 32 + d
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (wg == 0) {
-            float mx[2] = {-INFINITY, -INFINITY}, zs[2] = {0.f, 0.f};       // running maximum (log2 domain) / denominator per half
-            uint32_t nctx[2] = {0u, 0u};                                     // ctx MMAs of each half issued so far (for CTX_DONE phases)
-            uint32_t nflush[2] = {0u, 0u};
-            for (uint32_t g = 0; g < NG; ++g) {
-                const uint32_t hf = g & 1u;
+        if (wg < 2) {
+            // the exponentials are the slowest stage: the two halves (4 heads each) run on their own warp-groups, each keeping the
+            // running maximum / denominator of its rows in registers; they alternate on the single P^T operand buffer
+            const uint32_t hf = (uint32_t)wg;
+            float mx = -INFINITY, zs = 0.f;               // running maximum (log2 domain) / denominator of this row
+            uint32_t nctx = 0u;                           // ctx MMAs of this half requested so far (CTX_DONE phases)
+            const uint32_t t_kt = lane_base + T_KT + 64u * hf;
+            const uint32_t tcx = lane_base + T_CTX + 128u * hf + 32u * (uint32_t)q;      // this row's own 32 x 32 context block
+            for (uint32_t g = hf; g < NG; g += 2) {
                 const int tl = (int)(g >> 1);
                 const bool first = seg_first(tl), last = seg_last(tl);
                 ptx::mbar_wait(bar_at(bars, B_KT_FULL + hf), (uint32_t)tl & 1u);
                 ptx::tc_fence_after();
-                float kv[64];
-                {
-                    uint32_t u[8][8];
+                // ---- pass A: maximum of this row over the 64 positions of the tile (W_k carries log2(e): log2 domain)
+                float tm = -INFINITY;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) tmem_ld8(lane_base + T_KT + 64u * hf + 8u * (uint32_t)c, u[c]);
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t u[4][8];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tmem_ld8(t_kt + 32u * (uint32_t)hh + 8u * (uint32_t)c, u[c]);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
+                    for (int c = 0; c < 4; ++c)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) kv[8 * c + j] = __uint_as_float(u[c][j]);       // log2 domain: W_k carries log2(e) (host packer)
+                        for (int j = 0; j < 8; ++j) tm = fmaxf(tm, __uint_as_float(u[c][j]));
                 }
-                ptx::tc_fence_before();
-                warp_arrive(bar_at(bars, B_KT_EMPTY + hf), lane);
-                if (first) { mx[hf] = -INFINITY; zs[hf] = 0.f; }
-                float tm = kv[0];
-#pragma unroll
-                for (int j = 1; j < 64; ++j) tm = fmaxf(tm, kv[j]);
+                if (first) { mx = -INFINITY; zs = 0.f; }
                 // re-base this row when its maximum grew by more than the threshold (always on the first tile of a segment, where
                 // nothing has been accumulated yet); the TMEM loads / stores are warp-collective: any lane -> whole warp
-                const bool grow = tm > mx[hf] + RESCALE_THRESHOLD;
+                const bool grow = tm > mx + RESCALE_THRESHOLD;
                 if (first) {
-                    mx[hf] = tm;
+                    mx = tm;
                 } else if (__any_sync(0xffffffffu, grow)) {
-                    const float nm = grow ? tm : mx[hf];
-                    const float sc = ex2(mx[hf] - nm);                       // 1 for the lanes that keep their maximum
-                    ptx::mbar_wait(bar_at(bars, B_CTX_DONE + hf), (nctx[hf] - 1u) & 1u);     // every context MMA of this half has landed
+                    const float nm = grow ? tm : mx;
+                    const float sc = ex2(mx - nm);                           // 1 for the lanes that keep their maximum
+                    ptx::mbar_wait(bar_at(bars, B_CTX_DONE + hf), (nctx - 1u) & 1u);         // every context MMA of this half has landed
                     ptx::tc_fence_after();
-                    const uint32_t tcx = lane_base + T_CTX + 128u * hf + 32u * (uint32_t)q;   // this row's own 32 x 32 block
                     uint32_t cu[4][8];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) tmem_ld8(tcx + 8u * (uint32_t)c, cu[c]);
@@ -310,34 +329,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_ctx_kernel(const __grid_c
                     }
                     tmem_st_wait();
                     ptx::tc_fence_before();
-                    zs[hf] *= sc;
-                    mx[hf] = nm;
+                    zs *= sc;
+                    mx = nm;
                 }
+                // ctx(g-1) (the other half's) has read the operand: P_FREE[hf] completes once per step of the other group
+                if (g > 0) ptx::mbar_wait(bar_at(bars, B_P_FREE + hf), (hf ? (uint32_t)tl : (uint32_t)tl - 1u) & 1u);
+                // ---- pass B: exponentials, 32 positions at a time -> 4 operand chunks of the hi and of the lo plane
                 float s0 = 0.f, s1 = 0.f;
-                const float m = mx[hf];
 #pragma unroll
-                for (int j = 0; j < 64; j += 2) {
-                    kv[j] = ex2(kv[j] - m); kv[j + 1] = ex2(kv[j + 1] - m);
-                    s0 += kv[j]; s1 += kv[j + 1];
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t u[4][8];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tmem_ld8(t_kt + 32u * (uint32_t)hh + 8u * (uint32_t)c, u[c]);
+                    ptx::tmem_ld_wait();
+                    if (hh == 1) {
+                        ptx::tc_fence_before();
+                        warp_arrive(bar_at(bars, B_KT_EMPTY + hf), lane);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float e[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) {
+                            e[j] = ex2(__uint_as_float(u[c][j]) - mx); e[j + 1] = ex2(__uint_as_float(u[c][j + 1]) - mx);
+                            s0 += e[j]; s1 += e[j + 1];
+                        }
+                        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                        split2(e[0], e[1], h0, l0);
+                        split2(e[2], e[3], h1, l1);
+                        split2(e[4], e[5], h2, l2);
+                        split2(e[6], e[7], h3, l3);
+                        const uint32_t off = sb + OFF_P + sw_off(r, 4 * hh + c);
+                        sts128(off, h0, h1, h2, h3);
+                        sts128(off + 16384, l0, l1, l2, l3);
+                    }
                 }
-                zs[hf] += s0 + s1;
-                if (g > 0) ptx::mbar_wait(bar_at(bars, B_P_FREE), (g - 1) & 1);      // ctx(g-1) has read the operand
-                store_row64_hilo(sb + OFF_P, 16384, r, kv);
+                zs += s0 + s1;
                 ptx::fence_proxy_async();
                 warp_arrive(bar_at(bars, B_P_READY), lane);
-                ++nctx[hf];
+                ++nctx;
                 if (last) {
                     // flush this row of the segment: 32 context values (un-normalised, relative to the row maximum), maximum, denominator
-                    ptx::mbar_wait(bar_at(bars, B_CTX_DONE + hf), (nctx[hf] - 1u) & 1u);
+                    ptx::mbar_wait(bar_at(bars, B_CTX_DONE + hf), (nctx - 1u) & 1u);
                     ptx::tc_fence_after();
-                    const uint32_t tcx = lane_base + T_CTX + 128u * hf + 32u * (uint32_t)q;
                     uint32_t cu[4][8];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) tmem_ld8(tcx + 8u * (uint32_t)c, cu[c]);
                     ptx::tmem_ld_wait();
                     ptx::tc_fence_before();
                     warp_arrive(bar_at(bars, B_CTX_EMPTY + hf), lane);
-                    ++nflush[hf];
                     const int tg = t_begin + tl;
                     const int frame = tg / a.tpf;
                     const int part = (int)blockIdx.x - (frame * a.tpf) / a.tpc;
@@ -347,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_ctx_kernel(const __grid_c
 #pragma unroll
                         for (int j = 0; j < 8; j += 2)
                             *reinterpret_cast<float2*>(dst + 8 * c + j) = make_float2(__uint_as_float(cu[c][j]), __uint_as_float(cu[c][j + 1]));
-                    *reinterpret_cast<float2*>(dst + 32) = make_float2(mx[hf], zs[hf]);
+                    *reinterpret_cast<float2*>(dst + 32) = make_float2(mx, zs);
                 }
             }
         } else {
@@ -356,21 +396,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_ctx_kernel(const __grid_c
                 const uint32_t tl = g >> 1;
                 ptx::mbar_wait(bar_at(bars, B_VT_FULL + hf), tl & 1u);
                 ptx::tc_fence_after();
-                float vv[64];
-                {
-                    uint32_t u[8][8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) tmem_ld8(lane_base + T_VT + 64u * hf + 8u * (uint32_t)c, u[c]);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) vv[8 * c + j] = __uint_as_float(u[c][j]);
-                }
-                ptx::tc_fence_before();
-                warp_arrive(bar_at(bars, B_VT_EMPTY + hf), lane);
                 if (g > 0) ptx::mbar_wait(bar_at(bars, B_V_FREE), (g - 1) & 1);
-                store_row64_hilo(sb + OFF_V, 16384, r, vv);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t u[4][8];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tmem_ld8(lane_base + T_VT + 64u * hf + 32u * (uint32_t)hh + 8u * (uint32_t)c, u[c]);
+                    ptx::tmem_ld_wait();
+                    if (hh == 1) {
+                        ptx::tc_fence_before();
+                        warp_arrive(bar_at(bars, B_VT_EMPTY + hf), lane);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                        split2(__uint_as_float(u[c][0]), __uint_as_float(u[c][1]), h0, l0);
+                        split2(__uint_as_float(u[c][2]), __uint_as_float(u[c][3]), h1, l1);
+                        split2(__uint_as_float(u[c][4]), __uint_as_float(u[c][5]), h2, l2);
+                        split2(__uint_as_float(u[c][6]), __uint_as_float(u[c][7]), h3, l3);
+                        const uint32_t off = sb + OFF_V + sw_off(r, 4 * hh + c);
+                        sts128(off, h0, h1, h2, h3);
+                        sts128(off + 16384, l0, l1, l2, l3);
+                    }
+                }
                 ptx::fence_proxy_async();
                 warp_arrive(bar_at(bars, B_V_READY), lane);
             }
@@ -495,7 +543,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_apply_kernel(const __grid
     if (warp == 1 && ptx::elect_one()) {
         ptx::mbar_init(bar_at(bars, B_W_FULL), 1);
         for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(bar_at(bars, B_XN_FULL + i), 4);
+            ptx::mbar_init(bar_at(bars, B_XN_FULL + i), 1);
             ptx::mbar_init(bar_at(bars, B_XN_EMPTY + i), 1);
             ptx::mbar_init(bar_at(bars, B_QS_READY + i), 4);
             ptx::mbar_init(bar_at(bars, B_QS_FREE + i), 1);
@@ -528,9 +576,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_apply_kernel(const __grid
         if (ptx::elect_one() && my_tiles > 0) {
             ptx::mbar_arrive_expect_tx(bar_at(bars, B_W_FULL), 65536);
             for (int i = 0; i < 4; ++i) bulk_copy_g2s(sb + OFF_WQ + i * 16384, a.wq + (size_t)i * 16384, 16384, bar_at(bars, B_W_FULL));
-            pdl_wait();                                   // G comes from the combine kernel
+            pdl_wait();                                   // G comes from the combine kernel, the Xn images from launch 1
+            auto load_xn = [&](uint32_t tl) {            // normalised rows of tile tl: one 32 KiB image (hi | lo plane)
+                const uint32_t xb = tl & 1u;
+                ptx::mbar_wait(bar_at(bars, B_XN_EMPTY + xb), ((tl >> 1) & 1u) ^ 1u);
+                ptx::mbar_arrive_expect_tx(bar_at(bars, B_XN_FULL + xb), 32768);
+                bulk_copy_g2s(sb + OFF_XN + xb * 32768, a.ximg + (size_t)tile_of(tl) * 32768, 32768, bar_at(bars, B_XN_FULL + xb));
+            };
+            load_xn(0);
             for (uint32_t g = 0; g < NG; ++g) {
                 const uint32_t s = g & 1u;
+                if ((g & 3u) == 0 && (g >> 2) + 1 < (uint32_t)my_tiles) load_xn((g >> 2) + 1);
                 const int frame = tile_of(g >> 2) / a.tpf;
                 ptx::mbar_wait(bar_at(bars, B_G_EMPTY + s), ((g >> 1) & 1u) ^ 1u);
                 ptx::mbar_arrive_expect_tx(bar_at(bars, B_G_FULL + s), 16384);
@@ -595,11 +651,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_apply_kernel(const __grid
             }
         }
     } else if (warp < 6) {
-        // ===================== LayerNorm producers + tile epilogue (warps 2-5) =====================
+        // ===================== tile epilogue (warps 2-5) =====================
         pdl_wait();
-        const int t128 = (int)threadIdx.x - 64;
-        const int l16 = t128 & 15, rg = t128 >> 4;      // 16 lanes per row, 8 rows per pass, 16 passes
-        const float4 gam = *reinterpret_cast<const float4*>(a.gamma + l16 * 4);
         const int eq = warp & 3, er = eq * 32 + lane;   // TMEM lane quarter / tile row of this thread
         const int ec = lane & 3;
         auto epilogue = [&](uint32_t tl) {
@@ -651,20 +704,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_apply_kernel(const __grid
                 }
             }
         };
-        for (uint32_t tl = 0; tl < (uint32_t)my_tiles; ++tl) {
-            const int64_t row0 = (int64_t)tile_of(tl) * 128;
-            float4 v[16];
-#pragma unroll
-            for (int p = 0; p < 16; ++p) v[p] = *reinterpret_cast<const float4*>(a.x + (row0 + p * 8 + rg) * FC + l16 * 4);
-            ln_rows<16>(v, gam, a.eps);
-            const uint32_t xb = tl & 1u;
-            ptx::mbar_wait(bar_at(bars, B_XN_EMPTY + xb), ((tl >> 1) & 1u) ^ 1u);
-            ln_store<16, 8>(v, sb + OFF_XN + xb * 32768, 16384, rg, l16);
-            ptx::fence_proxy_async();
-            warp_arrive(bar_at(bars, B_XN_FULL + xb), lane);
-            if (tl > 0) epilogue(tl - 1);
-        }
-        if (my_tiles > 0) epilogue((uint32_t)my_tiles - 1);
+        for (uint32_t tl = 0; tl < (uint32_t)my_tiles; ++tl) epilogue(tl);
     } else {
         // ===================== two softmax warp-groups: WG w handles the chunks with (chunk & 1) == w =====================
         const int tc = (int)threadIdx.x - 192;
@@ -724,15 +764,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) linattn_apply_kernel(const __grid
 }  // namespace
 
 int lfdm_attn_linear_fused(const float* x, const float* gamma, const void* wk_packed, const void* wv_packed, const void* wq_packed,
-                           const float* wout, const float* out_bias, float* partials, void* g_images, float* out_f32,
-                           void* out_sb, int64_t out_plane, int frames, int pos, int c, int heads, float eps, void* stream) {
-    if (!x || !gamma || !wk_packed || !wv_packed || !wq_packed || !wout || !partials || !g_images || (!out_f32 && !out_sb))
+                           const float* wout, const float* out_bias, float* partials, void* g_images, void* xn_images,
+                           float* out_f32, void* out_sb, int64_t out_plane, int frames, int pos, int c, int heads, float eps,
+                           void* stream) {
+    if (!x || !gamma || !wk_packed || !wv_packed || !wq_packed || !wout || !partials || !g_images || !xn_images || (!out_f32 && !out_sb))
         return LFDM_E_BADARG;
     if (c != FC || heads != HEADS || frames < 1 || pos < 128 || (pos % 128) != 0) return LFDM_E_UNSUPP;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wk_packed) | reinterpret_cast<uintptr_t>(wv_packed) |
          reinterpret_cast<uintptr_t>(wq_packed) | reinterpret_cast<uintptr_t>(wout) | reinterpret_cast<uintptr_t>(gamma) |
          reinterpret_cast<uintptr_t>(out_bias) | reinterpret_cast<uintptr_t>(out_f32) | reinterpret_cast<uintptr_t>(out_sb) |
-         reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(g_images)) & 15)
+         reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(g_images) | reinterpret_cast<uintptr_t>(xn_images)) & 15)
         return LFDM_E_UNSUPP;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static PerDeviceOnce once;
@@ -752,7 +793,7 @@ int lfdm_attn_linear_fused(const float* x, const float* gamma, const void* wk_pa
     a.x = x; a.gamma = gamma;
     a.wk = reinterpret_cast<const uint8_t*>(wk_packed); a.wv = reinterpret_cast<const uint8_t*>(wv_packed);
     a.wq = reinterpret_cast<const uint8_t*>(wq_packed); a.wout = wout; a.out_bias = out_bias;
-    a.part = partials; a.gimg = reinterpret_cast<uint8_t*>(g_images);
+    a.part = partials; a.gimg = reinterpret_cast<uint8_t*>(g_images); a.ximg = reinterpret_cast<uint8_t*>(xn_images);
     a.out_f32 = out_f32; a.out_sb = reinterpret_cast<bf16*>(out_sb); a.out_plane = out_plane;
     a.frames = frames; a.pos = pos; a.eps = eps;
     // ---- launch 1: 64-row tiles, contiguous ranges
@@ -763,7 +804,7 @@ int lfdm_attn_linear_fused(const float* x, const float* gamma, const void* wk_pa
     while ((tpf1 + tpc1 - 1) / tpc1 + 1 > MAXP) ++tpc1;
     grid1 = (tiles1 + tpc1 - 1) / tpc1;
     a.tiles = tiles1; a.tpc = tpc1; a.tpf = tpf1;
-    LFDM_LAUNCH_PDL(linattn_ctx_kernel, dim3(grid1), dim3(NTHREADS), (size_t)l1::SMEM_BYTES, st, a);
+    LFDM_LAUNCH_PDL(linattn_ctx_kernel, dim3(grid1), dim3(NTHREADS1), (size_t)l1::SMEM_BYTES, st, a);
     // ---- launch 2
     LFDM_LAUNCH_PDL(linattn_combine_kernel, dim3(4, frames), dim3(256), (size_t)0, st, a, tpc1, tpf1);
     // ---- launch 3: 128-row tiles, round-robin

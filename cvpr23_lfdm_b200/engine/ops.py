@@ -300,13 +300,14 @@ def pack_fused_linear_attention(qkv_w, out_w):
 
 def attn_linear_fused(x, gamma, packed, out_bias, out_f32, out_sb, frames, pos, eps, work=None):
     """returns (rc, work): the C-ABI code (0, or L.E_UNSUPP when the geometry is not covered) and the work-space tensors
-    (partials, g_images) so that callers can keep them across calls"""
+    (partials, g_images, xn_images) so that callers can keep them across calls"""
     wk, wv, wq, wout = packed
     if work is None or work[0].shape[0] != frames:
         work = (torch.empty((frames, LINATTN_MAXP, 256, 34), device=x.device),
-                torch.empty((frames, 65536), dtype=torch.uint8, device=x.device))
+                torch.empty((frames, 65536), dtype=torch.uint8, device=x.device),
+                torch.empty((frames * pos // 128, 32768), dtype=torch.uint8, device=x.device))
     rc = lib().lfdm_attn_linear_fused(ptr(x), ptr(gamma), ptr(wk), ptr(wv), ptr(wq), ptr(wout), ptr(out_bias), ptr(work[0]), ptr(work[1]),
-                                      ptr(out_f32), ptr(out_sb.t) if out_sb is not None else None,
+                                      ptr(work[2]), ptr(out_f32), ptr(out_sb.t) if out_sb is not None else None,
                                       out_sb.plane if out_sb is not None else 0, frames, pos, x.shape[1], 8, eps, stream())
     if rc != L.E_UNSUPP:
         check(rc, "lfdm_attn_linear_fused")

@@ -141,13 +141,15 @@ int lfdm_attn_temporal_fused(const float* x, const float* gamma, const void* wq_
  * x / out rows [frame * pos + p][c], frames independent.  c == 64, heads == 8 (x 32), pos % 128 == 0 only (LFDM_E_UNSUPP
  * otherwise: the caller then composes lfdm_layernorm / lfdm_conv / lfdm_attn_linear).  wk / wv / wq_packed: split-bf16
  * operand images built by the host packer (engine/ops.py: pack_fused_linear_attention); wout: [64][256] fp32.
- * Work space owned by the caller (no allocation inside): partials [frames][LFDM_LINATTN_MAXP][256][34] fp32 and
- * g_images [frames][65536] bytes (per frame: the context folded with to_out, B operand of the apply pass).
+ * Work space owned by the caller (no allocation inside): partials [frames][LFDM_LINATTN_MAXP][256][34] fp32,
+ * g_images [frames][65536] bytes (per frame: the context folded with to_out, B operand of the apply pass) and
+ * xn_images [frames * pos / 128][32768] bytes (LayerNorm(x) as split-bf16 operand images, written by pass 1, read by pass 3).
  * Three launches on `stream` (context partials / merge / apply).                                                          */
 #define LFDM_LINATTN_MAXP 4
 int lfdm_attn_linear_fused(const float* x, const float* gamma, const void* wk_packed, const void* wv_packed, const void* wq_packed,
-                           const float* wout, const float* out_bias, float* partials, void* g_images, float* out_f32,
-                           void* out_sb, int64_t out_plane, int frames, int pos, int c, int heads, float eps, void* stream);
+                           const float* wout, const float* out_bias, float* partials, void* g_images, void* xn_images,
+                           float* out_f32, void* out_sb, int64_t out_plane, int frames, int pos, int c, int heads, float eps,
+                           void* stream);
 
 /* --- embeddings ---------------------------------------------------------------------------------------------- */
 /* y[r][n] = act_out( sum_k act_in(x[r][k]) W[n][k] + b[n] ), small-M GEMV-class (time_mlp :422-428, block mlp :217-220).
