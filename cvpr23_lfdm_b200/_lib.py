@@ -31,6 +31,7 @@ class ConvDesc(C.Structure):
         ("sb_shift", C.c_void_p), ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("rows_per_sample", C.c_int32),
         ("rot_cos", C.c_void_p), ("rot_sin", C.c_void_p), ("rot_frames", C.c_int32), ("rot_rows_per_frame", C.c_int32),
         ("rot_cols", C.c_int32), ("rot_scale_cols", C.c_int32), ("rot_scale", C.c_float),
+        ("sk_workspace", C.c_void_p), ("sk_workspace_bytes", C.c_int64), ("sk_flags", C.c_void_p), ("sk_slots", C.c_int32),
     ]
 
 

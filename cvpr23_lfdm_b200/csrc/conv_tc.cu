@@ -65,6 +65,11 @@ struct TcArgs {
     double* gn_stats;
     int32_t gn_cpg, gn_groups;
     int64_t rows_per_sample;
+    // stream-K (generic path): the flat (tile, K-block) space is cut into equal contiguous ranges, one per CTA; a tile cut in two
+    // is finished by the CTA that owns its end, the other one hands over its partial accumulator through sk_ws / sk_flag
+    int32_t sk;                      // K-blocks per CTA (0 = off: whole tiles, round-robin)
+    float* sk_ws;                    // [grid][128][bn] fp32 partial accumulators
+    int32_t* sk_flag;                // [grid] 0 / 1, left at 0 by the consumer
     const float* rot_cos;            // fused rotary of a temporal qkv projection (TMA-store epilogue only), see lfdm_conv_desc
     const float* rot_sin;
     int32_t rot_frames, rot_rows_per_frame, rot_cols, rot_scale_cols;
@@ -228,6 +233,47 @@ __device__ __forceinline__ void epi_block32(const TcArgs& a, float* stage, const
     __syncwarp();      // stage is reused by the next block
 }
 
+// ---- stream-K work list of one CTA.  Range [s, e) of the flat K-block space; natural segments are the pieces of consecutive
+// tiles inside it.  The piece at the END of the range that stops short of its tile's end (a HEAD: the next CTA finishes that
+// tile) is processed FIRST and the piece at the START that begins inside a tile (a TAIL: finishes the tile with the previous
+// CTA's partial) LAST, with the whole tiles in between: the partial a TAIL needs was published after at most one tile's worth
+// of K-blocks, while its consumer gets there after a whole range (>= one tile: host) -- nobody ever waits.  (HEAD first,
+// TAIL second measured +25 us: a CTA with a short HEAD reaches its TAIL long before a neighbour with a long HEAD publishes.)
+// Every range holds at least one whole tile's worth of K-blocks, so a tile is never cut into more than two pieces.
+struct SkSeg { int tile, kb0, kb1; };
+struct SkList {
+    int s, e, n_kb, t0, nseg, has_head, has_tail, n_mid;
+    __device__ SkList(int cta, int q, int n_kb_, int total_tiles) {
+        n_kb = n_kb_;
+        const long long tot = (long long)total_tiles * n_kb;
+        long long s64 = (long long)cta * q, e64 = s64 + q;
+        if (s64 > tot) s64 = tot;
+        if (e64 > tot) e64 = tot;
+        s = (int)s64; e = (int)e64;
+        t0 = s / n_kb;
+        nseg = e > s ? (e - 1) / n_kb - t0 + 1 : 0;
+        has_head = (nseg > 1 && (e % n_kb) != 0) ? 1 : 0;
+        has_tail = (nseg > 0 && (s % n_kb) != 0) ? 1 : 0;
+        n_mid = nseg - has_head - has_tail;
+    }
+    __device__ SkSeg at(int i) const {           // i-th piece in processing order: [HEAD] whole tiles ... [TAIL]
+        int j;
+        if (has_head && i == 0) {
+            j = nseg - 1;
+        } else {
+            const int k = i - has_head;
+            j = k < n_mid ? k + has_tail : 0;
+        }
+        const int tile = t0 + j;
+        const int lo = tile * n_kb, hi = lo + n_kb;
+        SkSeg g;
+        g.tile = tile;
+        g.kb0 = (s > lo ? s : lo) - lo;
+        g.kb1 = (e < hi ? e : hi) - lo;
+        return g;
+    }
+};
+
 template <int BN, int STAGES, bool WIDE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
     constexpr int B_BYTES = BN * BK * 2;
@@ -297,7 +343,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int total_tiles = a.m_tiles * a.n_tiles;
     // tiles are dealt round-robin: at any instant the CTAs sweep ~gridDim consecutive tiles, i.e. one contiguous window of the
     // activation tensor (measured ~8 % faster than giving every CTA its own contiguous range: DRAM/L2 locality across CTAs)
-    const int my_count = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const SkList skl((int)blockIdx.x, a.sk, n_kb > 0 ? n_kb : 1, total_tiles);
+    const int my_count = a.sk ? skl.nseg : (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -329,18 +376,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
         } else if (ptx::elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int it = 0; it < my_count; ++it) {
+                int tile, kb0 = 0, kb1 = n_kb;
+                if (a.sk) { const SkSeg sg = skl.at(it); tile = sg.tile; kb0 = sg.kb0; kb1 = sg.kb1; }
+                else tile = (int)blockIdx.x + it * (int)gridDim.x;
                 const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
                 const int w_t = m_tile % a.tiles_w;
                 const int h_t = (m_tile / a.tiles_w) % a.tiles_h;
                 const int nf_t = m_tile / (a.tiles_w * a.tiles_h);
                 const int w0 = w_t * a.bw, h0 = h_t * a.bh, nf0 = nf_t * a.bnf, n0 = n_tile * BN;
-                for (int tap = 0; tap < a.n_taps; ++tap) {
+                for (int tap = kb0 / kb_per_tap; tap < a.n_taps && tap * kb_per_tap < kb1; ++tap) {
                     const int dy = a.tap_dy[tap], dx = a.tap_dx[tap], mp = a.tap_map[tap];
                     for (int src = 0; src < 2; ++src) {
                         const CUtensorMap* tm = &a.tmA[src * 4 + mp];
                         const int kbase = src ? a.chunks[0] * BK : 0;
                         for (int ch = 0; ch < a.chunks[src]; ++ch) {
+                            const int kb = tap * kb_per_tap + (src ? a.chunks[0] : 0) + ch;
+                            if (kb < kb0 || kb >= kb1) continue;
                             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* s = smem + stage * STAGE_BYTES;
                             ptx::mbar_arrive_expect_tx(&full_bar[stage], ((a.dbg & 1) ? 0 : 2 * A_BYTES) + ((a.dbg & 2) ? 0 : 2 * B_BYTES));
@@ -439,14 +491,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             int stage = 0; uint32_t phase = 0;
             uint64_t da_hi = d0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (; it < my_count; ++it) {
+                int nkb_seg = n_kb;
+                if (a.sk) { const SkSeg sg = skl.at(it); nkb_seg = sg.kb1 - sg.kb0; }
                 const int as = it % ACC;
                 const uint32_t aphase = (it / ACC) & 1;
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * DCOLS;
                 uint32_t acc = 0u;
-                for (int kb = 0; kb < n_kb; ++kb) {
+                for (int kb = 0; kb < nkb_seg; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint64_t da_lo = da_hi + D_ALO, db_hi = da_hi + D_B;
@@ -494,7 +548,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             cur_sample = next_sample;
         };
         for (int it = grp; it < my_count; it += 2) {
-            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            int tile;
+            bool sk_head = false, sk_tail = false;       // this piece hands its partial over / finishes a tile with the previous CTA's
+            if (a.sk) {
+                const SkSeg sg = skl.at(it);
+                tile = sg.tile;
+                sk_head = sg.kb1 < n_kb;
+                sk_tail = sg.kb0 > 0;
+            } else {
+                tile = (int)blockIdx.x + it * (int)gridDim.x;
+            }
             const int as = it % ACC;
             const uint32_t aphase = (it / ACC) & 1;
             if (a.dbg & 128) {
@@ -515,7 +578,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const int64_t orow = ((int64_t)nf * a.ho_full + (h * a.mul + a.off_h)) * a.wo_full + (w * a.mul + a.off_w);
             int64_t rrow = orow;
             if (a.res_bcast_f > 0) rrow = (orow / ((int64_t)a.res_bcast_f * a.p_out)) * a.p_out + (orow % a.p_out);
-            if (a.gn_stats) {
+            if (a.gn_stats && !sk_head) {
                 const int bsample = (int)(__shfl_sync(0xffffffffu, orow, 0) / a.rows_per_sample);   // tile-uniform (128 | rows_per_sample)
                 if (bsample != cur_sample) gn_flush(bsample);
             }
@@ -540,6 +603,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             ptx::mbar_wait(&tfull_bar[as], aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * DCOLS);
+            // stream-K hand-over: row r of the [128][BN] fp32 slot of the producing CTA
+            float* sk_row = nullptr;
+            if (sk_head) sk_row = a.sk_ws + ((size_t)blockIdx.x * BM + r) * BN;
+            if (sk_tail) {
+                sk_row = a.sk_ws + ((size_t)(blockIdx.x - 1) * BM + r) * BN;
+                if (tig == 0) {
+                    int v;
+                    do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a.sk_flag + (blockIdx.x - 1)) : "memory"); } while (v == 0);
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            }
             if constexpr (BN >= 32) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -556,6 +630,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         for (int j = 0; j < 16; ++j) {
                             r0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(s0[j]));
                             r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(s1[j]));
+                        }
+                    }
+                    if (sk_head) {           // partial accumulator of this row -> the slot (fp32, 128 contiguous bytes per chunk)
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            *reinterpret_cast<uint4*>(sk_row + c0 + j) = make_uint4(r0[j], r0[j + 1], r0[j + 2], r0[j + 3]);
+                            *reinterpret_cast<uint4*>(sk_row + c0 + 16 + j) = make_uint4(r1[j], r1[j + 1], r1[j + 2], r1[j + 3]);
+                        }
+                        continue;
+                    }
+                    if (sk_tail) {           // + the first part of the K range, computed by the previous CTA (L2, not L1)
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 p0 = __ldcg(reinterpret_cast<const float4*>(sk_row + c0 + j));
+                            const float4 p1 = __ldcg(reinterpret_cast<const float4*>(sk_row + c0 + 16 + j));
+                            r0[j] = __float_as_uint(__uint_as_float(r0[j]) + p0.x); r0[j + 1] = __float_as_uint(__uint_as_float(r0[j + 1]) + p0.y);
+                            r0[j + 2] = __float_as_uint(__uint_as_float(r0[j + 2]) + p0.z); r0[j + 3] = __float_as_uint(__uint_as_float(r0[j + 3]) + p0.w);
+                            r1[j] = __float_as_uint(__uint_as_float(r1[j]) + p1.x); r1[j + 1] = __float_as_uint(__uint_as_float(r1[j + 1]) + p1.y);
+                            r1[j + 2] = __float_as_uint(__uint_as_float(r1[j + 2]) + p1.z); r1[j + 3] = __float_as_uint(__uint_as_float(r1[j + 3]) + p1.w);
                         }
                     }
                     if (a.tma_store) {
@@ -635,6 +728,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
+            if (sk_head) {
+                // every row of the slot is written and fenced before one thread publishes it
+                __threadfence();
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                if (tig == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.sk_flag + blockIdx.x), "r"(1) : "memory");
+            }
+            if (sk_tail) {
+                // all 128 threads have read the slot: re-arm the flag for the next launch
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                if (tig == 0) a.sk_flag[blockIdx.x - 1] = 0;
+            }
         }
         if (a.gn_stats) gn_flush(-1);
         if (a.tma_store && lane == 0) ptx::tma_store_wait0();
@@ -883,6 +987,27 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
         int rc;
         const int n_kb = taps_per_launch * (a.chunks[0] + a.chunks[1]);
         const bool wide = n_kb >= 3;          // MMA/smem-bound tiles: wide 2-MMA scheme; short-K GEMMs: deeper accumulator ring
+        // ---- stream-K: few, long tiles whose last wave is mostly empty (4x4 / 8x8 levels: 160 / 320 tiles of 72 / 36 K-blocks on
+        // 148 SMs) are cut at K-block granularity into one equal range per CTA
+        a.sk = 0;
+        {
+            static const bool allow = (getenv("LFDM_CONV_NO_STREAMK") == nullptr);       // A/B switch
+            int sms = 0, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (sms <= 0) sms = 148;
+            const int total = a.m_tiles * a.n_tiles;
+            if (allow && d->sk_workspace && d->sk_flags && !a.halo && n_launch == 1 && wide && bn >= 64 && n_kb >= 8 && total > sms) {
+                const int waves = (total + sms - 1) / sms;
+                const double ideal = (double)total / sms;
+                const long long need = (long long)sms * BM * bn * 4;
+                if ((waves - ideal) / waves > 0.08 && need <= d->sk_workspace_bytes && sms <= d->sk_slots) {
+                    a.sk = (int)(((long long)total * n_kb + sms - 1) / sms);      // >= n_kb because total > sms
+                    a.sk_ws = reinterpret_cast<float*>(d->sk_workspace);
+                    a.sk_flag = d->sk_flags;
+                }
+            }
+        }
         switch (bn) {
             case 128: rc = wide ? launch<128, 3, true>(a, st) : launch<128, 3, false>(a, st); break;
             case 64: rc = wide ? launch<64, 4, true>(a, st) : launch<64, 4, false>(a, st); break;

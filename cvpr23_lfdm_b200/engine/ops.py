@@ -23,6 +23,21 @@ def split_planes(w):
     return torch.stack([hi, lo], 0).contiguous()
 
 
+STREAM_K = os.environ.get("LFDM_CONV_NO_STREAMK") is None
+_SK_WS = {}
+
+
+def streamk_workspace(dev):
+    """one stream-K work space per device (lfdm_conv_desc.sk_*): every conv of the stream shares it (kernels are ordered)"""
+    key = (dev.type, dev.index)
+    ws = _SK_WS.get(key)
+    if ws is None:
+        slots = 256
+        ws = (torch.empty(slots * 128 * 128, dtype=torch.float32, device=dev), torch.zeros(slots, dtype=torch.int32, device=dev), slots)
+        _SK_WS[key] = ws
+    return ws
+
+
 class ConvLayer:
     """One convolution / linear layer with weights packed for both engines.
 
@@ -137,6 +152,9 @@ class ConvLayer:
                   out_f32=out_f32, f32_act=f32_act, out_sb=out_sb.t if out_sb is not None else None,
                   out_plane=out_sb.plane if out_sb is not None else 0, sb_act=sb_act, sb_scale=sb_scale,
                   sb_shift=sb_shift, gn_stats=None, gn_cpg=0, rows_per_sample=rows_per_sample)
+        if STREAM_K and self.w_sb is not None and all_sb:
+            ws, flags, slots = streamk_workspace(self.w_sb.device)
+            kw.update(sk_workspace=ws, sk_workspace_bytes=ws.numel() * 4, sk_flags=flags, sk_slots=slots)
         self.rot_applied = False
         if rot is not None:
             kw.update(rot_cos=rot[0], rot_sin=rot[1], rot_frames=int(rot[2]), rot_rows_per_frame=int(rot[3]),

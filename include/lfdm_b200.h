@@ -90,6 +90,14 @@ typedef struct lfdm_conv_desc {
     const float* rot_sin;
     int32_t      rot_frames, rot_rows_per_frame, rot_cols, rot_scale_cols;
     float        rot_scale;
+    /* stream-K work space of the TC engine (optional; NULL = whole tiles only).  Layers with few long tiles (4x4 / 8x8 levels)
+     * are cut into one equal K-block range per CTA; a tile cut in two is finished by the CTA that owns its end and the other
+     * CTA hands over its fp32 partial accumulator: sk_workspace >= #SMs * 128 * 128 * 4 bytes, sk_flags = sk_slots (>= #SMs)
+     * int32 zeros (the kernel leaves them at zero).  One work space can serve every conv of a stream.             */
+    void*        sk_workspace;
+    int64_t      sk_workspace_bytes;
+    int32_t*     sk_flags;
+    int32_t      sk_slots;
 } lfdm_conv_desc;
 
 int lfdm_conv(const lfdm_conv_desc* d, int engine, void* stream);

@@ -160,6 +160,10 @@ TC_CASES = [
     dict(n=2, cins=[64], cout=128, h=64, w=32, k=3, pad=1, residual=True),                        # halo mode, 16 row tiles
     dict(n=2, cins=[64], cout=64, h=16, w=16, k=3, pad=1, mode=2, reflect=True),                  # NATOPS up-conv: reflect == clamp on the low-res map
     dict(n=8, cins=[256], cout=256, h=4, w=4, k=3, pad=1, mode=2, reflect=True, f32_act=1),       # ... 4x4 -> 8x8, BN=128 (8 frames per 128-row tile)
+    # stream-K (more tiles than SMs, last wave mostly empty): tiles cut between CTAs, partial accumulators handed over
+    dict(n=320, cins=[512], cout=512, h=4, w=4, k=3, pad=1, gn_groups=8, fps=40, f32_only=True),  # 160 tiles x 72 K-blocks (the 4x4 level)
+    dict(n=320, cins=[256], cout=256, h=8, w=8, k=3, pad=1, residual=True),                       # 320 tiles x 36 K-blocks (the 8x8 level)
+    dict(n=640, cins=[64], cout=64, h=8, w=8, k=3, pad=1, gn_groups=8, fps=20),                   # 320 tiles x 9 K-blocks, BN = 64
 ]
 
 
