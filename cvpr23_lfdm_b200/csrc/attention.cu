@@ -212,223 +212,14 @@ __global__ void __launch_bounds__(128) attn_softmax_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Tensor-core softmax attention for 17 <= L <= 40 (the temporal attention over F = 40 frames): one warp per
-// (sequence, head); S = Q K^T and O = P V run on mma.sync.m16n8k8 TF32 with the 3xTF32 split
-// (x = hi + lo, hi.hi + hi.lo + lo.hi, fp32 accumulate) => fp32-class accuracy at ~2.5x fewer issued instructions than
-// the CUDA-core tiling above.  tcgen05 does not fit here: its minimum tile is 64/128 rows per MMA and every
-// (position, head) problem is an independent 40x40x32 product.
+// Tensor-core softmax attention for 17 <= L <= 40 (the temporal attention over F = 40 frames at the C >= 128 levels; the
+// C = 64 levels run the fused tcgen05 block of attn_fused.cu): one warp per (sequence, head) on mma.sync.m16n8k16 bf16 with
+// the split-bf16 x3 scheme of the conv engine (x = hi + lo: hi.hi + hi.lo + lo.hi, fp32 accumulate); the softmaxed scores
+// never leave registers: the C fragments of S = Q K^T are exactly the A fragments of O = P V.
+// (History: CUDA-core tiling 0.53 ms -> 3xTF32 m16n8k8 -> bf16 m16n8k16 0.47 -> the ldmatrix kernel below 0.42 ms per
+// 32x32 call; the two intermediate kernels were removed in round 2, the numbers are in profiles/r01_*.)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int ML = 40;              // padded sequence length of this kernel (5 n-tiles of 8; M padded to 48 = 3 m-tiles)
-constexpr int VPM = 40;             // V row pitch: conflict-free B-fragment loads (bank = 8 t + g)
-constexpr int PPM = 44;             // P row pitch
-
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&bh)[2],
-                                     const uint32_t (&bl)[2]) {
-    mma_tf32(d, al, bh);
-    mma_tf32(d, ah, bl);
-    mma_tf32(d, ah, bh);
-}
-
-__global__ void __launch_bounds__(128, 3) attn_softmax_mma_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
-                                                                  int64_t out_plane, float* __restrict__ out_f32,
-                                                                  int64_t n_seq, int L, int heads, int64_t inner,
-                                                                  int64_t outer_stride, int64_t inner_stride,
-                                                                  int64_t row_stride, const float* __restrict__ rot_cos,
-                                                                  const float* __restrict__ rot_sin,
-                                                                  const float* __restrict__ pos_bias) {
-    extern __shared__ __align__(16) float s_dyn[];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sq = s_dyn + (size_t)w * (2 * ML * QP + ML * VPM);     // Q [40][36] | K [40][36] | V [40][40]
-    float* sk = sq + ML * QP;
-    float* sv = sk + ML * QP;
-    float* sp = sq;                                               // P [48][44] / O [40][36] alias the dead Q/K tiles
-    const int64_t unit = (int64_t)blockIdx.x * 4 + w;
-    if (unit >= n_seq * heads) return;
-    const int64_t s = unit / heads;
-    const int h = (int)(unit - s * heads);
-    const int hid = heads * DH;
-    const int64_t base = (s / inner) * outer_stride + (s % inner) * inner_stride;
-    const float scale = 0.17677669529663687f;  // 32^-0.5
-
-    // ---- gather q/k/v rows with cp.async (everything in flight at once), zero the padding rows
-    {
-        const float* src0 = qkv + base * (3 * hid) + h * DH;
-        const int64_t rstep = row_stride * (3 * hid);
-        for (int idx = lane; idx < L * 8; idx += 32) {
-            const int j = idx >> 3, seg = idx & 7;
-            const float* sr = src0 + (int64_t)j * rstep + seg * 4;
-            cp_async16(sq + j * QP + seg * 4, sr);
-            cp_async16(sk + j * QP + seg * 4, sr + hid);
-            cp_async16(sv + j * VPM + seg * 4, sr + 2 * hid);
-        }
-        cp_async_commit();
-        for (int idx = lane; idx < (ML - L) * 8; idx += 32) {
-            const int j = L + (idx >> 3), seg = idx & 7;
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(sq + j * QP + seg * 4) = z;
-            *reinterpret_cast<float4*>(sk + j * QP + seg * 4) = z;
-            *reinterpret_cast<float4*>(sv + j * VPM + seg * 4) = z;
-        }
-        cp_async_wait<0>();
-        __syncwarp();
-        for (int idx = lane; idx < L * (DH / 2); idx += 32) {     // q *= scale; rotary (reference :325-331)
-            const int j = idx >> 4, pr = idx & 15;
-            float2 q2 = *reinterpret_cast<float2*>(sq + j * QP + 2 * pr);
-            q2.x *= scale; q2.y *= scale;
-            if (rot_cos) {
-                const float c = rot_cos[j * (DH / 2) + pr], sn = rot_sin[j * (DH / 2) + pr];
-                float2 k2 = *reinterpret_cast<float2*>(sk + j * QP + 2 * pr);
-                const float qx = q2.x * c - q2.y * sn, qy = q2.y * c + q2.x * sn;
-                const float kx = k2.x * c - k2.y * sn, ky = k2.y * c + k2.x * sn;
-                q2 = make_float2(qx, qy);
-                *reinterpret_cast<float2*>(sk + j * QP + 2 * pr) = make_float2(kx, ky);
-            }
-            *reinterpret_cast<float2*>(sq + j * QP + 2 * pr) = q2;
-        }
-    }
-    __syncwarp();
-
-    const int g = lane >> 2, t = lane & 3;
-    // ---- S = Q K^T : 3 m-tiles x 5 n-tiles, K = 32 in 4 steps.  fragment layouts of mma.m16n8k8 (row.col):
-    //      A: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  B: b0 (k=t, n=g) b1 (k=t+4, n=g);  C: (g, 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1)
-    float acc[3][5][4];
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 5; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-        uint32_t bh[5][2], bl[5][2];
-#pragma unroll
-        for (int nt = 0; nt < 5; ++nt) {
-            split_tf32(sk[(g + 8 * nt) * QP + 8 * ks + t], bh[nt][0], bl[nt][0]);
-            split_tf32(sk[(g + 8 * nt) * QP + 8 * ks + t + 4], bh[nt][1], bl[nt][1]);
-        }
-#pragma unroll
-        for (int mt = 0; mt < 3; ++mt) {
-            const int r0 = 16 * mt + g, r1 = (16 * mt + g + 8 < ML) ? 16 * mt + g + 8 : ML - 1;   // rows >= 40: clamped (unused)
-            uint32_t ah[4], al[4];
-            split_tf32(sq[r0 * QP + 8 * ks + t], ah[0], al[0]);
-            split_tf32(sq[r1 * QP + 8 * ks + t], ah[1], al[1]);
-            split_tf32(sq[r0 * QP + 8 * ks + t + 4], ah[2], al[2]);
-            split_tf32(sq[r1 * QP + 8 * ks + t + 4], ah[3], al[3]);
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt) mma3(acc[mt][nt], ah, al, bh[nt], bl[nt]);
-        }
-    }
-    __syncwarp();                  // Q/K fully consumed: P may overwrite them
-    // ---- bias + row softmax on the C fragments (a row lives in the 4 lanes that share g), P -> smem
-    const float* pb = pos_bias ? pos_bias + (int64_t)h * L * L : nullptr;
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int i = 16 * mt + g + 8 * half;
-            const bool row_ok = i < L;
-            float mx = -INFINITY;
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = 8 * nt + 2 * t + e;
-                    float v = acc[mt][nt][2 * half + e];
-                    if (pb && row_ok && j < L) v += pb[i * L + j];
-                    v = (j < L) ? v : -INFINITY;
-                    acc[mt][nt][2 * half + e] = v;
-                    mx = fmaxf(mx, v);
-                }
-            }
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            float sum = 0.f;
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float ex = __expf(acc[mt][nt][2 * half + e] - mx);   // ex2.approx: rel. error ~1e-6, inside the 1e-3 budget
-                    acc[mt][nt][2 * half + e] = ex;
-                    sum += ex;
-                }
-            }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            const float inv = 1.f / sum;
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt)
-                *reinterpret_cast<float2*>(sp + i * PPM + 8 * nt + 2 * t) =
-                    make_float2(acc[mt][nt][2 * half] * inv, acc[mt][nt][2 * half + 1] * inv);
-        }
-    }
-    __syncwarp();
-    // ---- O = P V : 3 m-tiles x 4 n-tiles (d), K = 40 (j) in 5 steps
-    float o[3][4][4];
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 5; ++ks) {
-        uint32_t bh[4][2], bl[4][2];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            split_tf32(sv[(8 * ks + t) * VPM + g + 8 * nt], bh[nt][0], bl[nt][0]);
-            split_tf32(sv[(8 * ks + t + 4) * VPM + g + 8 * nt], bh[nt][1], bl[nt][1]);
-        }
-#pragma unroll
-        for (int mt = 0; mt < 3; ++mt) {
-            const int r0 = 16 * mt + g, r1 = 16 * mt + g + 8;       // P has 48 rows
-            uint32_t ah[4], al[4];
-            split_tf32(sp[r0 * PPM + 8 * ks + t], ah[0], al[0]);
-            split_tf32(sp[r1 * PPM + 8 * ks + t], ah[1], al[1]);
-            split_tf32(sp[r0 * PPM + 8 * ks + t + 4], ah[2], al[2]);
-            split_tf32(sp[r1 * PPM + 8 * ks + t + 4], ah[3], al[3]);
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) mma3(o[mt][nt], ah, al, bh[nt], bl[nt]);
-        }
-    }
-    __syncwarp();                  // P consumed: stage O over it for coalesced row stores
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int i = 16 * mt + g + 8 * half;
-            if (i < ML) {
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
-                    *reinterpret_cast<float2*>(sp + i * QP + 8 * nt + 2 * t) = make_float2(o[mt][nt][2 * half], o[mt][nt][2 * half + 1]);
-            }
-        }
-    __syncwarp();
-    for (int idx = lane; idx < L * 8; idx += 32) {
-        const int i = idx >> 3, seg = idx & 7;
-        const float4 v = *reinterpret_cast<const float4*>(sp + i * QP + seg * 4);
-        const int64_t oi = (base + (int64_t)i * row_stride) * hid + h * DH + seg * 4;
-        if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi) = v;
-        if (out_sb) store_sb4(out_sb, out_plane, oi, v);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Same problem on mma.sync.m16n8k16 bf16 with the split-bf16 x3 scheme of the conv engine (x = hi + lo): twice the
-// MACs per issued MMA of the TF32 form (the legacy tensor path is the limiter of that kernel), and the softmaxed
-// scores never leave registers: the C fragments of S = Q K^T are exactly the A fragments of O = P V.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int QP2 = 40;             // Q/K row pitch: conflict-free float2 fragment loads (bank = 8 g + 2 t per half-warp)
-constexpr int VP2 = 36;             // V row pitch: conflict-free scalar B-fragment loads (bank = 8 t + g)
 
 __device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
@@ -436,6 +227,7 @@ __device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t& hi, uin
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -448,201 +240,6 @@ __device__ __forceinline__ void mma3_bf16(float (&d)[4], const uint32_t (&ah)[4]
     mma_bf16(d, ah, bh);
 }
 
-__global__ void __launch_bounds__(128, 3) attn_softmax_mma16_kernel(const float* __restrict__ qkv, bf16* __restrict__ out_sb,
-                                                                    int64_t out_plane, float* __restrict__ out_f32,
-                                                                    int64_t n_seq, int L, int heads, int64_t inner,
-                                                                    int64_t outer_stride, int64_t inner_stride,
-                                                                    int64_t row_stride, const float* __restrict__ rot_cos,
-                                                                    const float* __restrict__ rot_sin,
-                                                                    const float* __restrict__ pos_bias) {
-    pdl_prologue_done();
-    extern __shared__ __align__(16) float s_dyn[];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sq = s_dyn + (size_t)w * (2 * ML * QP2 + ML * VP2);    // Q [40][40] | K [40][40] | V [40][36]
-    float* sk = sq + ML * QP2;
-    float* sv = sk + ML * QP2;
-    const int64_t unit = (int64_t)blockIdx.x * 4 + w;
-    if (unit >= n_seq * heads) return;
-    const int64_t s = unit / heads;
-    const int h = (int)(unit - s * heads);
-    const int hid = heads * DH;
-    const int64_t base = (s / inner) * outer_stride + (s % inner) * inner_stride;
-    const float scale = 0.17677669529663687f;  // 32^-0.5
-
-    {
-        const float* src0 = qkv + base * (3 * hid) + h * DH;
-        const int64_t rstep = row_stride * (3 * hid);
-        for (int idx = lane; idx < L * 8; idx += 32) {
-            const int j = idx >> 3, seg = idx & 7;
-            const float* sr = src0 + (int64_t)j * rstep + seg * 4;
-            cp_async16(sq + j * QP2 + seg * 4, sr);
-            cp_async16(sk + j * QP2 + seg * 4, sr + hid);
-            cp_async16(sv + j * VP2 + seg * 4, sr + 2 * hid);
-        }
-        cp_async_commit();
-        for (int idx = lane; idx < (ML - L) * 8; idx += 32) {
-            const int j = L + (idx >> 3), seg = idx & 7;
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(sq + j * QP2 + seg * 4) = z;
-            *reinterpret_cast<float4*>(sk + j * QP2 + seg * 4) = z;
-            *reinterpret_cast<float4*>(sv + j * VP2 + seg * 4) = z;
-        }
-        cp_async_wait<0>();
-        __syncwarp();
-        for (int idx = lane; idx < L * (DH / 2); idx += 32) {     // q *= scale; rotary (reference :325-331)
-            const int j = idx >> 4, pr = idx & 15;
-            float2 q2 = *reinterpret_cast<float2*>(sq + j * QP2 + 2 * pr);
-            q2.x *= scale; q2.y *= scale;
-            if (rot_cos) {
-                const float c = rot_cos[j * (DH / 2) + pr], sn = rot_sin[j * (DH / 2) + pr];
-                float2 k2 = *reinterpret_cast<float2*>(sk + j * QP2 + 2 * pr);
-                const float qx = q2.x * c - q2.y * sn, qy = q2.y * c + q2.x * sn;
-                const float kx = k2.x * c - k2.y * sn, ky = k2.y * c + k2.x * sn;
-                q2 = make_float2(qx, qy);
-                *reinterpret_cast<float2*>(sk + j * QP2 + 2 * pr) = make_float2(kx, ky);
-            }
-            *reinterpret_cast<float2*>(sq + j * QP2 + 2 * pr) = q2;
-        }
-    }
-    __syncwarp();
-
-    const int g = lane >> 2, t = lane & 3;
-    // m16n8k16 fragments: A a0 (g, 2t..2t+1) a1 (g+8, 2t..) a2 (g, 2t+8..) a3 (g+8, 2t+8..);
-    //                     B b0 (k = 2t..2t+1, n = g) b1 (k = 2t+8.., n = g);  C (g, 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1)
-    float acc[3][5][4];
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 5; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-        uint32_t bh[5][2], bl[5][2];
-#pragma unroll
-        for (int nt = 0; nt < 5; ++nt) {
-            const float2 k0 = *reinterpret_cast<const float2*>(sk + (g + 8 * nt) * QP2 + 16 * ks + 2 * t);
-            const float2 k1 = *reinterpret_cast<const float2*>(sk + (g + 8 * nt) * QP2 + 16 * ks + 2 * t + 8);
-            split_bf16x2(k0.x, k0.y, bh[nt][0], bl[nt][0]);
-            split_bf16x2(k1.x, k1.y, bh[nt][1], bl[nt][1]);
-        }
-#pragma unroll
-        for (int mt = 0; mt < 3; ++mt) {
-            const int r0 = 16 * mt + g, r1 = (16 * mt + g + 8 < ML) ? 16 * mt + g + 8 : ML - 1;   // rows >= 40: clamped (unused)
-            uint32_t ah[4], al[4];
-            const float2 q0 = *reinterpret_cast<const float2*>(sq + r0 * QP2 + 16 * ks + 2 * t);
-            const float2 q1 = *reinterpret_cast<const float2*>(sq + r1 * QP2 + 16 * ks + 2 * t);
-            const float2 q2 = *reinterpret_cast<const float2*>(sq + r0 * QP2 + 16 * ks + 2 * t + 8);
-            const float2 q3 = *reinterpret_cast<const float2*>(sq + r1 * QP2 + 16 * ks + 2 * t + 8);
-            split_bf16x2(q0.x, q0.y, ah[0], al[0]);
-            split_bf16x2(q1.x, q1.y, ah[1], al[1]);
-            split_bf16x2(q2.x, q2.y, ah[2], al[2]);
-            split_bf16x2(q3.x, q3.y, ah[3], al[3]);
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt) mma3_bf16(acc[mt][nt], ah, al, bh[nt], bl[nt]);
-        }
-    }
-    // ---- bias + row softmax in registers (a row lives in the 4 lanes that share g)
-    const float* pb = pos_bias ? pos_bias + (int64_t)h * L * L : nullptr;
-    const bool pair_ok = (L & 1) == 0 && (reinterpret_cast<uintptr_t>(pos_bias) & 7) == 0;
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int i = 16 * mt + g + 8 * half;
-            const bool row_ok = i < L;
-            float mx = -INFINITY;
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt) {
-                const int j0 = 8 * nt + 2 * t;
-                float2 b2 = make_float2(0.f, 0.f);
-                if (pb && row_ok) {
-                    if (pair_ok) { if (j0 < L) b2 = *reinterpret_cast<const float2*>(pb + i * L + j0); }   // L even: (j0, j0+1) both < L
-                    else { if (j0 < L) b2.x = pb[i * L + j0]; if (j0 + 1 < L) b2.y = pb[i * L + j0 + 1]; }
-                }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    float v = acc[mt][nt][2 * half + e] + (e ? b2.y : b2.x);
-                    v = (j0 + e < L) ? v : -INFINITY;
-                    acc[mt][nt][2 * half + e] = v;
-                    mx = fmaxf(mx, v);
-                }
-            }
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            float sum = 0.f;
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float ex = __expf(acc[mt][nt][2 * half + e] - mx);   // ex2.approx: rel. error ~1e-6, inside the 1e-3 budget
-                    acc[mt][nt][2 * half + e] = ex;
-                    sum += ex;
-                }
-            }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            const float inv = 1.f / sum;
-#pragma unroll
-            for (int nt = 0; nt < 5; ++nt) { acc[mt][nt][2 * half] *= inv; acc[mt][nt][2 * half + 1] *= inv; }
-        }
-    }
-    // ---- O = P V : A fragments straight from the C fragments of S; K = 40 padded to 48 (3 k16 steps)
-    float o[3][4][4];
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 3; ++ks) {
-        uint32_t bh[4][2], bl[4][2];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            const int j0 = 16 * ks + 2 * t, j1 = j0 + 8;
-            const float v00 = sv[j0 * VP2 + g + 8 * nt], v01 = sv[(j0 + 1) * VP2 + g + 8 * nt];
-            float v10 = 0.f, v11 = 0.f;
-            if (j1 < ML) { v10 = sv[j1 * VP2 + g + 8 * nt]; v11 = sv[(j1 + 1) * VP2 + g + 8 * nt]; }
-            split_bf16x2(v00, v01, bh[nt][0], bl[nt][0]);
-            split_bf16x2(v10, v11, bh[nt][1], bl[nt][1]);
-        }
-#pragma unroll
-        for (int mt = 0; mt < 3; ++mt) {
-            uint32_t ah[4], al[4];
-            split_bf16x2(acc[mt][2 * ks][0], acc[mt][2 * ks][1], ah[0], al[0]);
-            split_bf16x2(acc[mt][2 * ks][2], acc[mt][2 * ks][3], ah[1], al[1]);
-            if (2 * ks + 1 < 5) {
-                split_bf16x2(acc[mt][2 * ks + 1][0], acc[mt][2 * ks + 1][1], ah[2], al[2]);
-                split_bf16x2(acc[mt][2 * ks + 1][2], acc[mt][2 * ks + 1][3], ah[3], al[3]);
-            } else {
-                ah[2] = al[2] = ah[3] = al[3] = 0u;
-            }
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) mma3_bf16(o[mt][nt], ah, al, bh[nt], bl[nt]);
-        }
-    }
-    __syncwarp();                  // every lane is done with Q/K: stage O over Q for coalesced row stores
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int i = 16 * mt + g + 8 * half;
-            if (i < ML) {
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
-                    *reinterpret_cast<float2*>(sq + i * QP2 + 8 * nt + 2 * t) = make_float2(o[mt][nt][2 * half], o[mt][nt][2 * half + 1]);
-            }
-        }
-    __syncwarp();
-    for (int idx = lane; idx < L * 8; idx += 32) {
-        const int i = idx >> 3, seg = idx & 7;
-        const float4 v = *reinterpret_cast<const float4*>(sq + i * QP2 + seg * 4);
-        const int64_t oi = (base + (int64_t)i * row_stride) * hid + h * DH + seg * 4;
-        if (out_f32) *reinterpret_cast<float4*>(out_f32 + oi) = v;
-        if (out_sb) store_sb4(out_sb, out_plane, oi, v);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // v2 of the same kernel: 16 resident warps per SM instead of 12 and ~40 % fewer instructions per unit.
@@ -1303,9 +900,7 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
     if (seq_len <= 16) return launch_attn_softmax<4, 2, true>(LFDM_ATTN_ARGS);
     if (seq_len <= 40) {
         static const bool use_mma = (getenv("LFDM_ATTN_SIMT") == nullptr);      // A/B switch: CUDA-core tiling instead
-        static const bool use_tf32 = (getenv("LFDM_ATTN_TF32") != nullptr);      // A/B switch: 3xTF32 m16n8k8 form
-        static const bool use_v1 = (getenv("LFDM_ATTN_V1") != nullptr);          // A/B switch: first mma.m16n8k16 kernel
-        if (use_mma && !use_tf32 && !use_v1 && seq_len >= 17) {
+        if (use_mma && seq_len >= 17) {
             const size_t smem = (size_t)4 * V2_WARP_BYTES;
             int rc = v2_set_smem(smem);
             if (rc) return rc;
@@ -1318,35 +913,6 @@ extern "C" int lfdm_attn_softmax(const float* qkv, void* out_sb, int64_t out_pla
                 LFDM_LAUNCH_PDL(attn_softmax_mma16v2_kernel<false>, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
                                 qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
                                 row_stride, rot_cos, rot_sin, pos_bias, 0);
-            return 0;
-        }
-        if (use_mma && !use_tf32) {
-            const size_t smem = sizeof(float) * 4 * (2 * ML * QP2 + ML * VP2);
-            static PerDeviceOnce once16;
-            if (once16.need()) {
-                cudaError_t e = cudaFuncSetAttribute(attn_softmax_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return (int)e;
-                once16.mark();
-            }
-            const int64_t units = n_seq * heads;
-            LFDM_LAUNCH_PDL(attn_softmax_mma16_kernel, dim3((unsigned)((units + 3) / 4)), dim3(128), smem, st,
-                            qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride,
-                            row_stride, rot_cos, rot_sin, pos_bias);
-            return 0;
-        }
-        if (use_mma) {
-            const size_t smem = sizeof(float) * 4 * (2 * ML * QP + ML * VPM);
-            static PerDeviceOnce once;
-            if (once.need()) {
-                cudaError_t e = cudaFuncSetAttribute(attn_softmax_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return (int)e;
-                once.mark();
-            }
-            const int64_t units = n_seq * heads;
-            attn_softmax_mma_kernel<<<(unsigned)((units + 3) / 4), 128, smem, st>>>(
-                qkv, (bf16*)out_sb, out_plane, out_f32, n_seq, seq_len, heads, inner, outer_stride, inner_stride, row_stride,
-                rot_cos, rot_sin, pos_bias);
-            LFDM_CHECK_LAUNCH();
             return 0;
         }
         return launch_attn_softmax<10, 5, true>(LFDM_ATTN_ARGS);
