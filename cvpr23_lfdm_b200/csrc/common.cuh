@@ -44,6 +44,30 @@ inline cudaError_t lfdm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 blo
     cfg.numAttrs = lfdm_pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
 }
+// same, launched as thread-block clusters of `cluster_x` CTAs (cluster_x <= 1: plain launch)
+template <typename... KArgs, typename... Args>
+inline cudaError_t lfdm_launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                           Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    memset(at, 0, sizeof(at));
+    int n = 0;
+    if (lfdm_pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 #define LFDM_LAUNCH_PDL(...)                                   \
     do {                                                      \
         cudaError_t e__ = lfdm_launch_pdl(__VA_ARGS__);       \

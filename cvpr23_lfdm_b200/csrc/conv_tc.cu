@@ -40,6 +40,8 @@ constexpr int NUM_THREADS = 384;     // warp0 TMA (A), warp1 MMA, warp2 TMEM all
 struct TcArgs {
     CUtensorMap tmA[8];              // [source*4 + parity view]
     CUtensorMap tmB;
+    CUtensorMap tmBh;                // weight tile cut in two (box rows = BN / 2): pair mode, each CTA fetches one half and multicasts it
+    int32_t pair;                    // 1: launched as clusters of 2 CTAs that walk the same (n_tile, K) sequence on adjacent M tiles
     CUtensorMap tmOut;               // fp32 [M][c_out], box {32 cols, 32 rows}, 128B swizzle (TMA-store epilogue)
     int32_t tma_store;
     int32_t dbg;                     // LFDM_CONV_DBG ablation bits (timing experiments only): 1 no A loads, 2 no B loads, 8 no TMA stores, 128 no epilogue body
@@ -323,7 +325,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         if (a.tma_store) ptx::prefetch_tensormap(&a.tmOut);
     }
     if (warp == 1 && ptx::elect_one()) {
-        for (int i = 0; i < MAXB; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+        // pair mode: a weight stage is written by BOTH CTAs (each multicasts its half), so it is free only when both MMAs are done
+        for (int i = 0; i < MAXB; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], a.pair ? 2 : 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&fullA_bar[i], 1); ptx::mbar_init(&emptyA_bar[i], 1); }
         for (int i = 0; i < ACC; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 128); }
         ptx::fence_barrier_init();
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (a.pair) ptx::cluster_sync_all();       // the peer's barriers exist before anything is multicast to them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();          // the producing kernel has completed: activations / residual / GroupNorm accumulators are safe to touch
@@ -343,8 +347,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int total_tiles = a.m_tiles * a.n_tiles;
     // tiles are dealt round-robin: at any instant the CTAs sweep ~gridDim consecutive tiles, i.e. one contiguous window of the
     // activation tensor (measured ~8 % faster than giving every CTA its own contiguous range: DRAM/L2 locality across CTAs)
-    const SkList skl((int)blockIdx.x, a.sk, n_kb > 0 ? n_kb : 1, total_tiles);
-    const int my_count = a.sk ? skl.nseg : (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // work units: tiles, or (pair mode) pairs of M-adjacent tiles with the same n_tile, one per CTA of the cluster
+    const int crank = a.pair ? (int)ptx::cluster_ctarank() : 0;
+    const int ncta = a.pair ? 2 : 1;
+    const int wid = (int)blockIdx.x / ncta, nw = (int)gridDim.x / ncta;
+    const int total_units = total_tiles / ncta;
+    auto unit_tile = [&](int u) { return a.pair ? ((2 * (u / a.n_tiles) + crank) * a.n_tiles + (u % a.n_tiles)) : u; };
+    const SkList skl(wid, a.sk, n_kb > 0 ? n_kb : 1, total_units);
+    const int my_count = a.sk ? skl.nseg : (total_units - wid + nw - 1) / nw;
+    const uint16_t pair_mask = 3;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -352,7 +363,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if constexpr (HALO_OK) {
                 if (ptx::elect_one()) {      // A producer: one halo copy per (dx, source, 64-channel chunk)
                     int sa = 0; uint32_t pa = 0;
-                    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    for (int it = 0; it < my_count; ++it) {
+                        const int tile = unit_tile(wid + it * nw);
                         const int m_tile = tile / a.n_tiles;
                         const int w_t = m_tile % a.tiles_w;
                         const int h_t = (m_tile / a.tiles_w) % a.tiles_h;
@@ -378,8 +390,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < my_count; ++it) {
                 int tile, kb0 = 0, kb1 = n_kb;
-                if (a.sk) { const SkSeg sg = skl.at(it); tile = sg.tile; kb0 = sg.kb0; kb1 = sg.kb1; }
-                else tile = (int)blockIdx.x + it * (int)gridDim.x;
+                if (a.sk) { const SkSeg sg = skl.at(it); tile = unit_tile(sg.tile); kb0 = sg.kb0; kb1 = sg.kb1; }
+                else tile = unit_tile(wid + it * nw);
                 const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
                 const int w_t = m_tile % a.tiles_w;
                 const int h_t = (m_tile / a.tiles_w) % a.tiles_h;
@@ -400,10 +412,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             ptx::tma_load_5d(s, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 0);
                             ptx::tma_load_5d(s + A_BYTES, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 1); }
                             if (!(a.dbg & 2)) {
+                            if (a.pair) {        // this CTA's half of the tile (rows crank * BN/2 ...), delivered to both CTAs
+                                uint8_t* sbh = s + 2 * A_BYTES + crank * (B_BYTES / 2);
+                                ptx::tma_load_4d_multicast(sbh, &a.tmBh, &full_bar[stage], kbase + ch * BK, n0 + crank * (BN / 2),
+                                                           a.tap_base + tap, 0, pair_mask);
+                                ptx::tma_load_4d_multicast(sbh + B_BYTES, &a.tmBh, &full_bar[stage], kbase + ch * BK, n0 + crank * (BN / 2),
+                                                           a.tap_base + tap, 1, pair_mask);
+                            } else {
                             ptx::tma_load_4d(s + 2 * A_BYTES, &a.tmB, &full_bar[stage], kbase + ch * BK, n0,
                                              a.tap_base + tap, 0);
                             ptx::tma_load_4d(s + 2 * A_BYTES + B_BYTES, &a.tmB, &full_bar[stage], kbase + ch * BK, n0,
-                                             a.tap_base + tap, 1); }
+                                             a.tap_base + tap, 1); } }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -415,7 +434,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         if constexpr (HALO_OK) {
             if (halo && ptx::elect_one()) {
                 int sb = 0; uint32_t pb = 0;
-                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int it = 0; it < my_count; ++it) {
+                    const int tile = unit_tile(wid + it * nw);
                     const int n0 = (tile % a.n_tiles) * BN;
                     for (int dxi = 0; dxi < 3; ++dxi)
                         for (int src = 0; src < 2; ++src) {
@@ -426,8 +446,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                     uint8_t* s = smem + 2 * A_HALO_STAGE + sb * (2 * B_BYTES);
                                     if (a.dbg & 2) { ptx::mbar_arrive_expect_tx(&full_bar[sb], 0); } else {
                                     ptx::mbar_arrive_expect_tx(&full_bar[sb], 2 * B_BYTES);
+                                    if (a.pair) {
+                                        uint8_t* sbh = s + crank * (B_BYTES / 2);
+                                        ptx::tma_load_4d_multicast(sbh, &a.tmBh, &full_bar[sb], kbase + ch * BK, n0 + crank * (BN / 2),
+                                                                   a.tap_base + dyi * 3 + dxi, 0, pair_mask);
+                                        ptx::tma_load_4d_multicast(sbh + B_BYTES, &a.tmBh, &full_bar[sb], kbase + ch * BK, n0 + crank * (BN / 2),
+                                                                   a.tap_base + dyi * 3 + dxi, 1, pair_mask);
+                                    } else {
                                     ptx::tma_load_4d(s, &a.tmB, &full_bar[sb], kbase + ch * BK, n0, a.tap_base + dyi * 3 + dxi, 0);
-                                    ptx::tma_load_4d(s + B_BYTES, &a.tmB, &full_bar[sb], kbase + ch * BK, n0, a.tap_base + dyi * 3 + dxi, 1); }
+                                    ptx::tma_load_4d(s + B_BYTES, &a.tmB, &full_bar[sb], kbase + ch * BK, n0, a.tap_base + dyi * 3 + dxi, 1); } }
                                     if (++sb == NB) { sb = 0; pb ^= 1; }
                                 }
                         }
@@ -446,7 +473,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 uint64_t dA = dA0, dB = dB0;
                 int it = 0;
                 const int groups = 3 * kb_per_tap;
-                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                for (; it < my_count; ++it) {
                     const int as = it % ACC;
                     const uint32_t aphase = (it / ACC) & 1;
                     ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -467,7 +494,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 ptx::umma_bf16(tmem_d, da_lo + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC, 1u);          // + A_lo.W_hi
                                 acc = 1u;
                             }
-                            ptx::umma_commit(&empty_bar[sb]);
+                            if (a.pair) ptx::umma_commit_multicast(&empty_bar[sb], pair_mask); else ptx::umma_commit(&empty_bar[sb]);
                             da_hi += dy_step;
                             dB += DB_STRIDE;
                             if (++sb == NB) { sb = 0; pb ^= 1; dB = dB0; }
@@ -518,7 +545,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         }
                         acc = 1u;
                     }
-                    ptx::umma_commit(&empty_bar[stage]);
+                    if (a.pair) ptx::umma_commit_multicast(&empty_bar[stage], pair_mask); else ptx::umma_commit(&empty_bar[stage]);
                     da_hi += D_STRIDE;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; da_hi = d0; }
                 }
@@ -552,11 +579,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             bool sk_head = false, sk_tail = false;       // this piece hands its partial over / finishes a tile with the previous CTA's
             if (a.sk) {
                 const SkSeg sg = skl.at(it);
-                tile = sg.tile;
+                tile = unit_tile(sg.tile);
                 sk_head = sg.kb1 < n_kb;
                 sk_tail = sg.kb0 > 0;
             } else {
-                tile = (int)blockIdx.x + it * (int)gridDim.x;
+                tile = unit_tile(wid + it * nw);
             }
             const int as = it % ACC;
             const uint32_t aphase = (it / ACC) & 1;
@@ -607,10 +634,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             float* sk_row = nullptr;
             if (sk_head) sk_row = a.sk_ws + ((size_t)blockIdx.x * BM + r) * BN;
             if (sk_tail) {
-                sk_row = a.sk_ws + ((size_t)(blockIdx.x - 1) * BM + r) * BN;
+                sk_row = a.sk_ws + ((size_t)(blockIdx.x - ncta) * BM + r) * BN;       // the same rank of the previous work unit
                 if (tig == 0) {
                     int v;
-                    do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a.sk_flag + (blockIdx.x - 1)) : "memory"); } while (v == 0);
+                    do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a.sk_flag + (blockIdx.x - ncta)) : "memory"); } while (v == 0);
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
             }
@@ -737,7 +764,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (sk_tail) {
                 // all 128 threads have read the slot: re-arm the flag for the next launch
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                if (tig == 0) a.sk_flag[blockIdx.x - 1] = 0;
+                if (tig == 0) a.sk_flag[blockIdx.x - ncta] = 0;
             }
         }
         if (a.gn_stats) gn_flush(-1);
@@ -746,6 +773,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (a.pair) ptx::cluster_sync_all();       // the peer may still multicast into this CTA's ring / arrive on its barriers
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -785,11 +813,12 @@ int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims
 }
 
 template <int BN, int STAGES, bool WIDE>
-int launch(const TcArgs& a, cudaStream_t st) {
+int launch(const TcArgs& a_in, cudaStream_t st) {
+    TcArgs a = a_in;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BN * BK * 2;
     constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 8 * 4096 + 256 + 512;   // + 8 staging tiles + barriers + GN accumulators
     static PerDeviceOnce once;
-    static int num_sms = 0;
+    static int num_sms = 0, max_clusters = 0;
     if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return (int)e;
@@ -797,11 +826,40 @@ int launch(const TcArgs& a, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
+        // clusters of 2 that can be resident at a time (GPCs with an odd number of usable SMs leave one SM out)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(num_sms & ~1)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM;
+        cudaLaunchAttribute at[1];
+        memset(at, 0, sizeof(at));
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, conv_tc_kernel<BN, STAGES, WIDE>, &cfg) != cudaSuccess || max_clusters <= 0) {
+            (void)cudaGetLastError();
+            max_clusters = num_sms / 2;
+        }
+        if (max_clusters > num_sms / 2) max_clusters = num_sms / 2;
         once.mark();
     }
     int total = a.m_tiles * a.n_tiles;
     int grid = total < num_sms ? total : num_sms;
-    LFDM_LAUNCH_PDL((conv_tc_kernel<BN, STAGES, WIDE>), dim3(grid), dim3(NUM_THREADS), (size_t)SMEM, st, a);
+    int units = total, workers = grid;          // work units (tiles / tile pairs) and the CTAs / clusters that walk them
+    if (a.pair) {                               // clusters of 2 CTAs, one pair of M-adjacent tiles per cluster and step
+        units = total / 2;
+        workers = units < max_clusters ? units : max_clusters;
+        grid = 2 * workers;
+    }
+    if (a.sk) {
+        // stream-K pays when the last wave is mostly empty; K-blocks per worker >= K-blocks per tile because units > workers
+        const int n_kb = a.sk;
+        const int waves = (units + workers - 1) / workers;
+        const double ideal = (double)units / workers;
+        a.sk = (units > workers && (waves - ideal) / waves > 0.08) ? (int)(((long long)units * n_kb + workers - 1) / workers) : 0;
+    }
+    cudaError_t e = lfdm_launch_pdl_cluster(conv_tc_kernel<BN, STAGES, WIDE>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM, st,
+                                            a.pair ? 2 : 1, a);
+    if (e != cudaSuccess) return (int)e;
     return 0;
 }
 
@@ -890,6 +948,9 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
         cuuint64_t strides[3] = {(cuuint64_t)cin_total * 2, (cuuint64_t)cin_total * c_out_pad * 2, (cuuint64_t)d->w_plane * 2};
         cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bn, 1, 1};
         int rc = make_map(&a.tmB, d->w_sb, 4, dims, strides, box);
+        if (rc) return rc;
+        cuuint32_t boxh[4] = {(cuuint32_t)BK, (cuuint32_t)(bn >= 16 ? bn / 2 : bn), 1, 1};
+        rc = make_map(&a.tmBh, d->w_sb, 4, dims, strides, boxh);
         if (rc) return rc;
     }
     // ---- TMA-store epilogue: plain F32 output (+bias, +GroupNorm sums), consecutive output rows per tile
@@ -987,6 +1048,13 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
         int rc;
         const int n_kb = taps_per_launch * (a.chunks[0] + a.chunks[1]);
         const bool wide = n_kb >= 3;          // MMA/smem-bound tiles: wide 2-MMA scheme; short-K GEMMs: deeper accumulator ring
+        // ---- pair mode: clusters of 2 CTAs on M-adjacent tiles of the same n_tile fetch the weight tile once (each CTA one half,
+        // multicast to both): the 3x3 layers are bound by L2 -> SM operand traffic, of which the weights are a third to two thirds
+        a.pair = 0;
+        {
+            static const bool allow = (getenv("LFDM_CONV_NO_PAIR") == nullptr);          // A/B switch
+            if (allow && wide && (bn == 64 || bn == 128) && n_kb >= 8 && (a.m_tiles % 2) == 0 && a.m_tiles * a.n_tiles >= 64) a.pair = 1;
+        }
         // ---- stream-K: few, long tiles whose last wave is mostly empty (4x4 / 8x8 levels: 160 / 320 tiles of 72 / 36 K-blocks on
         // 148 SMs) are cut at K-block granularity into one equal range per CTA
         a.sk = 0;
@@ -996,16 +1064,13 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (sms <= 0) sms = 148;
-            const int total = a.m_tiles * a.n_tiles;
-            if (allow && d->sk_workspace && d->sk_flags && !a.halo && n_launch == 1 && wide && bn >= 64 && n_kb >= 8 && total > sms) {
-                const int waves = (total + sms - 1) / sms;
-                const double ideal = (double)total / sms;
-                const long long need = (long long)sms * BM * bn * 4;
-                if ((waves - ideal) / waves > 0.08 && need <= d->sk_workspace_bytes && sms <= d->sk_slots) {
-                    a.sk = (int)(((long long)total * n_kb + sms - 1) / sms);      // >= n_kb because total > sms
-                    a.sk_ws = reinterpret_cast<float*>(d->sk_workspace);
-                    a.sk_flag = d->sk_flags;
-                }
+            // eligibility only: the split itself (K-blocks per worker) is fixed in launch<>(), where the number of resident
+            // CTAs / clusters is known
+            if (allow && d->sk_workspace && d->sk_flags && !a.halo && n_launch == 1 && wide && bn >= 64 && n_kb >= 8 &&
+                (long long)sms * BM * bn * 4 <= d->sk_workspace_bytes && sms <= d->sk_slots) {
+                a.sk = n_kb;                                          // marker: K-blocks per tile
+                a.sk_ws = reinterpret_cast<float*>(d->sk_workspace);
+                a.sk_flag = d->sk_flags;
             }
         }
         switch (bn) {
