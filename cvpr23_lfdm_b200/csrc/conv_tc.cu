@@ -40,8 +40,8 @@ constexpr int NUM_THREADS = 384;     // warp0 TMA (A), warp1 MMA, warp2 TMEM all
 struct TcArgs {
     CUtensorMap tmA[8];              // [source*4 + parity view]
     CUtensorMap tmB;
-    CUtensorMap tmBh;                // weight tile cut in two (box rows = BN / 2): pair mode, each CTA fetches one half and multicasts it
-    int32_t pair;                    // 1: launched as clusters of 2 CTAs that walk the same (n_tile, K) sequence on adjacent M tiles
+    CUtensorMap tmBh;                // weight tile cut in two (box rows = BN / 2): pair mode, each CTA holds half of the rows of B
+    int32_t pair;                    // 1: clusters of 2 CTAs = one cta_group::2 MMA pair: M = 256 (two M-adjacent tiles), B split in two
     CUtensorMap tmOut;               // fp32 [M][c_out], box {32 cols, 32 rows}, 128B swizzle (TMA-store epilogue)
     int32_t tma_store;
     int32_t dbg;                     // LFDM_CONV_DBG ablation bits (timing experiments only): 1 no A loads, 2 no B loads, 8 no TMA stores, 128 no epilogue body
@@ -292,6 +292,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     static_assert(ACC * DCOLS <= 512, "accumulator ring exceeds TMEM");
     constexpr uint32_t IDESC_WIDE = ptx::make_idesc_bf16(BM, 2 * BN);
     constexpr uint32_t IDESC = ptx::make_idesc_bf16(BM, BN);
+    // CTA pair (cta_group::2): M = 256 = this CTA's 128 rows + the peer's, every CTA holds HALF of the rows of each B operand
+    // at the same shared-memory offset: rank 0 [W_hi[0:BN/2] ; W_lo[BN/2:BN]], rank 1 [W_hi[BN/2:BN] ; W_lo[0:BN/2]].
+    //   wide MMA   (A_hi, N = 2 BN): accumulator column blocks (BN/2 wide)  [hi0 | lo1 | hi1 | lo0]
+    //   narrow MMA (A_lo, N = BN)  : the first BN/2 rows of both CTAs = W_hi[0:BN/2], W_hi[BN/2:BN] -> added to blocks 0 and 1
+    // so blocks 0 + 3 sum to output columns [0, BN/2) and blocks 1 + 2 to [BN/2, BN).  Per K-step and CTA the shared-memory port
+    // carries A 8 KiB + B 3/4 BN x 32 B instead of A 8 KiB + B 3/2 BN x 32 B, and the weight fills are halved.
+    constexpr uint32_t IDESC_WIDE2 = ptx::make_idesc_bf16(2 * BM, 2 * BN);
+    constexpr uint32_t IDESC2 = ptx::make_idesc_bf16(2 * BM, BN);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -325,19 +333,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         if (a.tma_store) ptx::prefetch_tensormap(&a.tmOut);
     }
     if (warp == 1 && ptx::elect_one()) {
-        // pair mode: a weight stage is written by BOTH CTAs (each multicasts its half), so it is free only when both MMAs are done
-        for (int i = 0; i < MAXB; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], a.pair ? 2 : 1); }
+        // pair mode: the "full" / "tmem empty" barriers of the EVEN CTA collect both CTAs (TMA bytes, epilogue threads); "empty" /
+        // "tmem full" are signalled in both CTAs by the multicast commits of the even CTA's MMA thread
+        for (int i = 0; i < MAXB; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&fullA_bar[i], 1); ptx::mbar_init(&emptyA_bar[i], 1); }
-        for (int i = 0; i < ACC; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 128); }
+        for (int i = 0; i < ACC; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], a.pair ? 256 : 128); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (a.pair) { ptx::tmem_alloc_2sm(tmem_ptr, TMEM_COLS); ptx::tmem_relinquish_2sm(); }
+        else { ptx::tmem_alloc(tmem_ptr, TMEM_COLS); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (a.pair) ptx::cluster_sync_all();       // the peer's barriers exist before anything is multicast to them
+    if (a.pair) ptx::cluster_sync_all();       // the peer's barriers exist before anything is signalled on them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();          // the producing kernel has completed: activations / residual / GroupNorm accumulators are safe to touch
@@ -376,6 +385,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 for (int ch = 0; ch < a.chunks[src]; ++ch) {
                                     ptx::mbar_wait(&emptyA_bar[sa], pa ^ 1);
                                     uint8_t* s = smem + sa * A_HALO_STAGE;
+                                    if (a.pair) {        // both CTAs' halo copies are counted on the even CTA's barrier
+                                        if (crank == 0) ptx::mbar_arrive_expect_tx(&fullA_bar[sa], 4 * a.halo_plane);
+                                        ptx::tma_load_5d_2sm(s, tm, &fullA_bar[sa], ch * BK, w0 + dxi - 1, h0 - 1, nf0, 0);
+                                        ptx::tma_load_5d_2sm(s + a.halo_plane, tm, &fullA_bar[sa], ch * BK, w0 + dxi - 1, h0 - 1, nf0, 1);
+                                    } else
                                     if (a.dbg & 1) { ptx::mbar_arrive_expect_tx(&fullA_bar[sa], 0); } else {
                                     ptx::mbar_arrive_expect_tx(&fullA_bar[sa], 2 * a.halo_plane);
                                     ptx::tma_load_5d(s, tm, &fullA_bar[sa], ch * BK, w0 + dxi - 1, h0 - 1, nf0, 0);
@@ -407,18 +421,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             if (kb < kb0 || kb >= kb1) continue;
                             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* s = smem + stage * STAGE_BYTES;
+                            if (a.pair) {
+                                // own A tile + own half of B ([W_hi rows of this rank ; W_lo rows of the other half]); bytes of both CTAs -> even CTA
+                                if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (2 * A_BYTES + B_BYTES));
+                                ptx::tma_load_5d_2sm(s, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 0);
+                                ptx::tma_load_5d_2sm(s + A_BYTES, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 1);
+                                ptx::tma_load_4d_2sm(s + 2 * A_BYTES, &a.tmBh, &full_bar[stage], kbase + ch * BK, n0 + crank * (BN / 2),
+                                                     a.tap_base + tap, 0);
+                                ptx::tma_load_4d_2sm(s + 2 * A_BYTES + B_BYTES / 2, &a.tmBh, &full_bar[stage], kbase + ch * BK,
+                                                     n0 + (1 - crank) * (BN / 2), a.tap_base + tap, 1);
+                            } else {
                             ptx::mbar_arrive_expect_tx(&full_bar[stage], ((a.dbg & 1) ? 0 : 2 * A_BYTES) + ((a.dbg & 2) ? 0 : 2 * B_BYTES));
                             if (!(a.dbg & 1)) {
                             ptx::tma_load_5d(s, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 0);
                             ptx::tma_load_5d(s + A_BYTES, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 1); }
                             if (!(a.dbg & 2)) {
-                            if (a.pair) {        // this CTA's half of the tile (rows crank * BN/2 ...), delivered to both CTAs
-                                uint8_t* sbh = s + 2 * A_BYTES + crank * (B_BYTES / 2);
-                                ptx::tma_load_4d_multicast(sbh, &a.tmBh, &full_bar[stage], kbase + ch * BK, n0 + crank * (BN / 2),
-                                                           a.tap_base + tap, 0, pair_mask);
-                                ptx::tma_load_4d_multicast(sbh + B_BYTES, &a.tmBh, &full_bar[stage], kbase + ch * BK, n0 + crank * (BN / 2),
-                                                           a.tap_base + tap, 1, pair_mask);
-                            } else {
                             ptx::tma_load_4d(s + 2 * A_BYTES, &a.tmB, &full_bar[stage], kbase + ch * BK, n0,
                                              a.tap_base + tap, 0);
                             ptx::tma_load_4d(s + 2 * A_BYTES + B_BYTES, &a.tmB, &full_bar[stage], kbase + ch * BK, n0,
@@ -444,17 +461,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 for (int dyi = 0; dyi < 3; ++dyi) {
                                     ptx::mbar_wait(&empty_bar[sb], pb ^ 1);
                                     uint8_t* s = smem + 2 * A_HALO_STAGE + sb * (2 * B_BYTES);
+                                    if (a.pair) {
+                                        if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[sb], 2 * B_BYTES);
+                                        ptx::tma_load_4d_2sm(s, &a.tmBh, &full_bar[sb], kbase + ch * BK, n0 + crank * (BN / 2),
+                                                             a.tap_base + dyi * 3 + dxi, 0);
+                                        ptx::tma_load_4d_2sm(s + B_BYTES / 2, &a.tmBh, &full_bar[sb], kbase + ch * BK, n0 + (1 - crank) * (BN / 2),
+                                                             a.tap_base + dyi * 3 + dxi, 1);
+                                    } else
                                     if (a.dbg & 2) { ptx::mbar_arrive_expect_tx(&full_bar[sb], 0); } else {
                                     ptx::mbar_arrive_expect_tx(&full_bar[sb], 2 * B_BYTES);
-                                    if (a.pair) {
-                                        uint8_t* sbh = s + crank * (B_BYTES / 2);
-                                        ptx::tma_load_4d_multicast(sbh, &a.tmBh, &full_bar[sb], kbase + ch * BK, n0 + crank * (BN / 2),
-                                                                   a.tap_base + dyi * 3 + dxi, 0, pair_mask);
-                                        ptx::tma_load_4d_multicast(sbh + B_BYTES, &a.tmBh, &full_bar[sb], kbase + ch * BK, n0 + crank * (BN / 2),
-                                                                   a.tap_base + dyi * 3 + dxi, 1, pair_mask);
-                                    } else {
                                     ptx::tma_load_4d(s, &a.tmB, &full_bar[sb], kbase + ch * BK, n0, a.tap_base + dyi * 3 + dxi, 0);
-                                    ptx::tma_load_4d(s + B_BYTES, &a.tmB, &full_bar[sb], kbase + ch * BK, n0, a.tap_base + dyi * 3 + dxi, 1); } }
+                                    ptx::tma_load_4d(s + B_BYTES, &a.tmB, &full_bar[sb], kbase + ch * BK, n0, a.tap_base + dyi * 3 + dxi, 1); }
                                     if (++sb == NB) { sb = 0; pb ^= 1; }
                                 }
                         }
@@ -462,9 +479,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
         }
     } else if (warp == 1 && halo) {
-        // ===================== halo mode: MMA issuer (one elected thread runs the whole loop) =====================
+        // ===================== halo mode: MMA issuer (one elected thread runs the whole loop; pair mode: of the even CTA) ========
         if constexpr (HALO_OK) {
-            if (ptx::elect_one()) {
+            if (crank == 0 && ptx::elect_one()) {
                 constexpr uint64_t DB_STRIDE = (2 * B_BYTES) >> 4;
                 const uint64_t dA0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem));
                 const uint64_t dB0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + 2 * A_HALO_STAGE));
@@ -490,20 +507,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             const uint64_t da_lo = da_hi + lo_step;
 #pragma unroll
                             for (int ks = 0; ks < BK / 16; ++ks) {
+                                if (a.pair) {
+                                    ptx::umma_bf16_2sm(tmem_d, da_hi + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_WIDE2, acc);
+                                    ptx::umma_bf16_2sm(tmem_d, da_lo + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC2, 1u);
+                                } else {
                                 ptx::umma_bf16(tmem_d, da_hi + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_WIDE, acc);   // A_hi.[W_hi;W_lo]
                                 ptx::umma_bf16(tmem_d, da_lo + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC, 1u);          // + A_lo.W_hi
+                                }
                                 acc = 1u;
                             }
-                            if (a.pair) ptx::umma_commit_multicast(&empty_bar[sb], pair_mask); else ptx::umma_commit(&empty_bar[sb]);
+                            if (a.pair) ptx::umma_commit_2sm(&empty_bar[sb], pair_mask); else ptx::umma_commit(&empty_bar[sb]);
                             da_hi += dy_step;
                             dB += DB_STRIDE;
                             if (++sb == NB) { sb = 0; pb ^= 1; dB = dB0; }
                         }
-                        ptx::umma_commit(&emptyA_bar[sa]);
+                        if (a.pair) ptx::umma_commit_2sm(&emptyA_bar[sa], pair_mask); else ptx::umma_commit(&emptyA_bar[sa]);
                         dA += (uint64_t)(A_HALO_STAGE >> 4);
                         if (++sa == 2) { sa = 0; pa ^= 1; dA = dA0; }
                     }
-                    ptx::umma_commit(&tfull_bar[as]);
+                    if (a.pair) ptx::umma_commit_2sm(&tfull_bar[as], pair_mask); else ptx::umma_commit(&tfull_bar[as]);
                 }
             }
         }
@@ -512,7 +534,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // The tensor-core queue is short: whatever the issuing thread executes between the last MMA of one stage and the
         // first of the next is exposed as tensor-pipe idle time (measured ~330 clk / stage with a per-stage elect + descriptor
         // rebuild, i.e. as long as the 8 MMAs of a BN = 64 stage).  Descriptors are therefore carried incrementally.
-        if (ptx::elect_one()) {
+        if (crank == 0 && ptx::elect_one()) {
             constexpr uint64_t D_STRIDE = STAGE_BYTES >> 4, D_ALO = A_BYTES >> 4, D_B = (2 * A_BYTES) >> 4;
             const uint64_t d0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem));
             int stage = 0; uint32_t phase = 0;
@@ -535,8 +557,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     for (int ks = 0; ks < BK / 16; ++ks) {
                         const uint64_t off = (uint64_t)(ks * 2);   // 16 bf16 = 32 B, encoded >> 4
                         if constexpr (WIDE) {
+                            if (a.pair) {
+                                ptx::umma_bf16_2sm(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE2, acc);
+                                ptx::umma_bf16_2sm(tmem_d, da_lo + off, db_hi + off, IDESC2, 1u);
+                            } else {
                             ptx::umma_bf16(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE, acc);      // A_hi.[W_hi;W_lo]
                             ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, 1u);            // + A_lo.W_hi
+                            }
                         } else {
                             const uint64_t db_lo = db_hi + (uint64_t)(B_BYTES >> 4);
                             ptx::umma_bf16(tmem_d, da_lo + off, db_hi + off, IDESC, acc);
@@ -545,11 +572,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         }
                         acc = 1u;
                     }
-                    if (a.pair) ptx::umma_commit_multicast(&empty_bar[stage], pair_mask); else ptx::umma_commit(&empty_bar[stage]);
+                    if (a.pair) ptx::umma_commit_2sm(&empty_bar[stage], pair_mask); else ptx::umma_commit(&empty_bar[stage]);
                     da_hi += D_STRIDE;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; da_hi = d0; }
                 }
-                ptx::umma_commit(&tfull_bar[as]);
+                if (a.pair) ptx::umma_commit_2sm(&tfull_bar[as], pair_mask); else ptx::umma_commit(&tfull_bar[as]);
             }
         }
     } else if (warp >= 4) {
@@ -648,8 +675,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     ptx::tmem_ld16(taddr + c0, r0);
                     ptx::tmem_ld16(taddr + c0 + 16, r1);
                     if constexpr (WIDE) {
-                        ptx::tmem_ld16(taddr + BN + c0, s0);
-                        ptx::tmem_ld16(taddr + BN + c0 + 16, s1);
+                        // partner column block of this chunk: [x | x + BN], or (pair mode, blocks [hi0 | lo1 | hi1 | lo0]) 0 <-> 3, 1 <-> 2
+                        const int sec = a.pair ? (c0 < BN / 2 ? c0 + BN + BN / 2 : c0 + BN / 2) : BN + c0;
+                        ptx::tmem_ld16(taddr + sec, s0);
+                        ptx::tmem_ld16(taddr + sec + 16, s1);
                     }
                     ptx::tmem_ld_wait();
                     if constexpr (WIDE) {
@@ -754,7 +783,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 epi_chunk16(a, r0, n0, orow, rrow, gn_acc, lane, vec_ok);
             }
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&tempty_bar[as]);
+            if (a.pair) ptx::mbar_arrive_leader(&tempty_bar[as]); else ptx::mbar_arrive(&tempty_bar[as]);
             if (sk_head) {
                 // every row of the slot is written and fenced before one thread publishes it
                 __threadfence();
@@ -776,7 +805,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (a.pair) ptx::cluster_sync_all();       // the peer may still multicast into this CTA's ring / arrive on its barriers
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (a.pair) ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -826,26 +855,30 @@ int launch(const TcArgs& a_in, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
-        // clusters of 2 that can be resident at a time (GPCs with an odd number of usable SMs leave one SM out)
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)(num_sms & ~1)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM;
-        cudaLaunchAttribute at[1];
-        memset(at, 0, sizeof(at));
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        if (cudaOccupancyMaxActiveClusters(&max_clusters, conv_tc_kernel<BN, STAGES, WIDE>, &cfg) != cudaSuccess || max_clusters <= 0) {
-            (void)cudaGetLastError();
-            max_clusters = num_sms / 2;
-        }
-        if (max_clusters > num_sms / 2) max_clusters = num_sms / 2;
+        max_clusters = num_sms / 2;
         once.mark();
     }
     int total = a.m_tiles * a.n_tiles;
     int grid = total < num_sms ? total : num_sms;
     int units = total, workers = grid;          // work units (tiles / tile pairs) and the CTAs / clusters that walk them
     if (a.pair) {                               // clusters of 2 CTAs, one pair of M-adjacent tiles per cluster and step
+        static PerDeviceOnce once_c;
+        if (once_c.need()) {
+            // clusters of 2 that can be resident at a time (GPCs with an odd number of usable SMs leave one SM out)
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)(num_sms & ~1)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM;
+            cudaLaunchAttribute at[1];
+            memset(at, 0, sizeof(at));
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int mc = 0;
+            if (cudaOccupancyMaxActiveClusters(&mc, conv_tc_kernel<BN, STAGES, WIDE>, &cfg) == cudaSuccess && mc > 0 && mc < max_clusters)
+                max_clusters = mc;
+            (void)cudaGetLastError();
+            once_c.mark();
+        }
         units = total / 2;
         workers = units < max_clusters ? units : max_clusters;
         grid = 2 * workers;
@@ -1048,11 +1081,15 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
         int rc;
         const int n_kb = taps_per_launch * (a.chunks[0] + a.chunks[1]);
         const bool wide = n_kb >= 3;          // MMA/smem-bound tiles: wide 2-MMA scheme; short-K GEMMs: deeper accumulator ring
-        // ---- pair mode: clusters of 2 CTAs on M-adjacent tiles of the same n_tile fetch the weight tile once (each CTA one half,
-        // multicast to both): the 3x3 layers are bound by L2 -> SM operand traffic, of which the weights are a third to two thirds
+        // ---- pair mode (cta_group::2): clusters of 2 CTAs on M-adjacent tiles of the same n_tile run one M = 256 MMA stream; each
+        // CTA holds half of the rows of every weight tile.  (Sharing the weight tile by TMA multicast with cta_group::1 MMAs was
+        // measured first: no gain -- the bound is the shared-memory port of each SM, not L2 -> SM traffic.)
         a.pair = 0;
         {
-            static const bool allow = (getenv("LFDM_CONV_NO_PAIR") == nullptr);          // A/B switch
+            // OFF by default: measured on B200 (profiles/r02_conv_pair_experiments.md) the CTA-pair form is 5-20 % SLOWER than
+            // independent CTAs on every 3x3 layer of the UNet, and sharing the weight tile by TMA multicast (cta_group::1 MMAs)
+            // changes nothing; LFDM_CONV_PAIR=1 turns it on for experiments.
+            static const bool allow = (getenv("LFDM_CONV_PAIR") != nullptr);
             if (allow && wide && (bn == 64 || bn == 128) && n_kb >= 8 && (a.m_tiles % 2) == 0 && a.m_tiles * a.n_tiles >= 64) a.pair = 1;
         }
         // ---- stream-K: few, long tiles whose last wave is mostly empty (4x4 / 8x8 levels: 160 / 320 tiles of 72 / 36 K-blocks on
