@@ -276,7 +276,8 @@ struct SkList {
     }
 };
 
-template <int BN, int STAGES, bool WIDE>
+// PAIR: the cta_group::2 build (must be launched as clusters of 2: a kernel that contains 2-CTA instructions is refused by a plain launch)
+template <int BN, int STAGES, bool WIDE, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -337,16 +338,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // "tmem full" are signalled in both CTAs by the multicast commits of the even CTA's MMA thread
         for (int i = 0; i < MAXB; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&fullA_bar[i], 1); ptx::mbar_init(&emptyA_bar[i], 1); }
-        for (int i = 0; i < ACC; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], a.pair ? 256 : 128); }
+        for (int i = 0; i < ACC; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], PAIR ? 256 : 128); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        if (a.pair) { ptx::tmem_alloc_2sm(tmem_ptr, TMEM_COLS); ptx::tmem_relinquish_2sm(); }
+        if constexpr (PAIR) { ptx::tmem_alloc_2sm(tmem_ptr, TMEM_COLS); ptx::tmem_relinquish_2sm(); }
         else { ptx::tmem_alloc(tmem_ptr, TMEM_COLS); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (a.pair) ptx::cluster_sync_all();       // the peer's barriers exist before anything is signalled on them
+    if constexpr (PAIR) ptx::cluster_sync_all();       // the peer's barriers exist before anything is signalled on them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();          // the producing kernel has completed: activations / residual / GroupNorm accumulators are safe to touch
@@ -357,11 +358,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // tiles are dealt round-robin: at any instant the CTAs sweep ~gridDim consecutive tiles, i.e. one contiguous window of the
     // activation tensor (measured ~8 % faster than giving every CTA its own contiguous range: DRAM/L2 locality across CTAs)
     // work units: tiles, or (pair mode) pairs of M-adjacent tiles with the same n_tile, one per CTA of the cluster
-    const int crank = a.pair ? (int)ptx::cluster_ctarank() : 0;
-    const int ncta = a.pair ? 2 : 1;
+    const int crank = PAIR ? (int)ptx::cluster_ctarank() : 0;
+    const int ncta = PAIR ? 2 : 1;
     const int wid = (int)blockIdx.x / ncta, nw = (int)gridDim.x / ncta;
     const int total_units = total_tiles / ncta;
-    auto unit_tile = [&](int u) { return a.pair ? ((2 * (u / a.n_tiles) + crank) * a.n_tiles + (u % a.n_tiles)) : u; };
+    auto unit_tile = [&](int u) { return PAIR ? ((2 * (u / a.n_tiles) + crank) * a.n_tiles + (u % a.n_tiles)) : u; };
     const SkList skl(wid, a.sk, n_kb > 0 ? n_kb : 1, total_units);
     const int my_count = a.sk ? skl.nseg : (total_units - wid + nw - 1) / nw;
     const uint16_t pair_mask = 3;
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 for (int ch = 0; ch < a.chunks[src]; ++ch) {
                                     ptx::mbar_wait(&emptyA_bar[sa], pa ^ 1);
                                     uint8_t* s = smem + sa * A_HALO_STAGE;
-                                    if (a.pair) {        // both CTAs' halo copies are counted on the even CTA's barrier
+                                    if constexpr (PAIR) {        // both CTAs' halo copies are counted on the even CTA's barrier
                                         if (crank == 0) ptx::mbar_arrive_expect_tx(&fullA_bar[sa], 4 * a.halo_plane);
                                         ptx::tma_load_5d_2sm(s, tm, &fullA_bar[sa], ch * BK, w0 + dxi - 1, h0 - 1, nf0, 0);
                                         ptx::tma_load_5d_2sm(s + a.halo_plane, tm, &fullA_bar[sa], ch * BK, w0 + dxi - 1, h0 - 1, nf0, 1);
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             if (kb < kb0 || kb >= kb1) continue;
                             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* s = smem + stage * STAGE_BYTES;
-                            if (a.pair) {
+                            if constexpr (PAIR) {
                                 // own A tile + own half of B ([W_hi rows of this rank ; W_lo rows of the other half]); bytes of both CTAs -> even CTA
                                 if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (2 * A_BYTES + B_BYTES));
                                 ptx::tma_load_5d_2sm(s, tm, &full_bar[stage], ch * BK, w0 + dx, h0 + dy, nf0, 0);
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 for (int dyi = 0; dyi < 3; ++dyi) {
                                     ptx::mbar_wait(&empty_bar[sb], pb ^ 1);
                                     uint8_t* s = smem + 2 * A_HALO_STAGE + sb * (2 * B_BYTES);
-                                    if (a.pair) {
+                                    if constexpr (PAIR) {
                                         if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[sb], 2 * B_BYTES);
                                         ptx::tma_load_4d_2sm(s, &a.tmBh, &full_bar[sb], kbase + ch * BK, n0 + crank * (BN / 2),
                                                              a.tap_base + dyi * 3 + dxi, 0);
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             const uint64_t da_lo = da_hi + lo_step;
 #pragma unroll
                             for (int ks = 0; ks < BK / 16; ++ks) {
-                                if (a.pair) {
+                                if constexpr (PAIR) {
                                     ptx::umma_bf16_2sm(tmem_d, da_hi + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC_WIDE2, acc);
                                     ptx::umma_bf16_2sm(tmem_d, da_lo + (uint64_t)(ks * 2), dB + (uint64_t)(ks * 2), IDESC2, 1u);
                                 } else {
@@ -516,16 +517,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 }
                                 acc = 1u;
                             }
-                            if (a.pair) ptx::umma_commit_2sm(&empty_bar[sb], pair_mask); else ptx::umma_commit(&empty_bar[sb]);
+                            if constexpr (PAIR) ptx::umma_commit_2sm(&empty_bar[sb], pair_mask); else ptx::umma_commit(&empty_bar[sb]);
                             da_hi += dy_step;
                             dB += DB_STRIDE;
                             if (++sb == NB) { sb = 0; pb ^= 1; dB = dB0; }
                         }
-                        if (a.pair) ptx::umma_commit_2sm(&emptyA_bar[sa], pair_mask); else ptx::umma_commit(&emptyA_bar[sa]);
+                        if constexpr (PAIR) ptx::umma_commit_2sm(&emptyA_bar[sa], pair_mask); else ptx::umma_commit(&emptyA_bar[sa]);
                         dA += (uint64_t)(A_HALO_STAGE >> 4);
                         if (++sa == 2) { sa = 0; pa ^= 1; dA = dA0; }
                     }
-                    if (a.pair) ptx::umma_commit_2sm(&tfull_bar[as], pair_mask); else ptx::umma_commit(&tfull_bar[as]);
+                    if constexpr (PAIR) ptx::umma_commit_2sm(&tfull_bar[as], pair_mask); else ptx::umma_commit(&tfull_bar[as]);
                 }
             }
         }
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     for (int ks = 0; ks < BK / 16; ++ks) {
                         const uint64_t off = (uint64_t)(ks * 2);   // 16 bf16 = 32 B, encoded >> 4
                         if constexpr (WIDE) {
-                            if (a.pair) {
+                            if constexpr (PAIR) {
                                 ptx::umma_bf16_2sm(tmem_d, da_hi + off, db_hi + off, IDESC_WIDE2, acc);
                                 ptx::umma_bf16_2sm(tmem_d, da_lo + off, db_hi + off, IDESC2, 1u);
                             } else {
@@ -572,11 +573,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         }
                         acc = 1u;
                     }
-                    if (a.pair) ptx::umma_commit_2sm(&empty_bar[stage], pair_mask); else ptx::umma_commit(&empty_bar[stage]);
+                    if constexpr (PAIR) ptx::umma_commit_2sm(&empty_bar[stage], pair_mask); else ptx::umma_commit(&empty_bar[stage]);
                     da_hi += D_STRIDE;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; da_hi = d0; }
                 }
-                if (a.pair) ptx::umma_commit_2sm(&tfull_bar[as], pair_mask); else ptx::umma_commit(&tfull_bar[as]);
+                if constexpr (PAIR) ptx::umma_commit_2sm(&tfull_bar[as], pair_mask); else ptx::umma_commit(&tfull_bar[as]);
             }
         }
     } else if (warp >= 4) {
@@ -676,7 +677,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     ptx::tmem_ld16(taddr + c0 + 16, r1);
                     if constexpr (WIDE) {
                         // partner column block of this chunk: [x | x + BN], or (pair mode, blocks [hi0 | lo1 | hi1 | lo0]) 0 <-> 3, 1 <-> 2
-                        const int sec = a.pair ? (c0 < BN / 2 ? c0 + BN + BN / 2 : c0 + BN / 2) : BN + c0;
+                        const int sec = PAIR ? (c0 < BN / 2 ? c0 + BN + BN / 2 : c0 + BN / 2) : BN + c0;
                         ptx::tmem_ld16(taddr + sec, s0);
                         ptx::tmem_ld16(taddr + sec + 16, s1);
                     }
@@ -783,7 +784,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 epi_chunk16(a, r0, n0, orow, rrow, gn_acc, lane, vec_ok);
             }
             ptx::tc_fence_before();
-            if (a.pair) ptx::mbar_arrive_leader(&tempty_bar[as]); else ptx::mbar_arrive(&tempty_bar[as]);
+            if constexpr (PAIR) ptx::mbar_arrive_leader(&tempty_bar[as]); else ptx::mbar_arrive(&tempty_bar[as]);
             if (sk_head) {
                 // every row of the slot is written and fenced before one thread publishes it
                 __threadfence();
@@ -802,10 +803,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (a.pair) ptx::cluster_sync_all();       // the peer may still multicast into this CTA's ring / arrive on its barriers
+    if constexpr (PAIR) ptx::cluster_sync_all();       // the peer may still multicast into this CTA's ring / arrive on its barriers
     if (warp == 2) {
         ptx::tc_fence_after();
-        if (a.pair) ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if constexpr (PAIR) ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -841,7 +842,7 @@ int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims
     return r == CUDA_SUCCESS ? 0 : (1000 + (int)r);
 }
 
-template <int BN, int STAGES, bool WIDE>
+template <int BN, int STAGES, bool WIDE, bool PAIR>
 int launch(const TcArgs& a_in, cudaStream_t st) {
     TcArgs a = a_in;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BN * BK * 2;
@@ -849,7 +850,7 @@ int launch(const TcArgs& a_in, cudaStream_t st) {
     static PerDeviceOnce once;
     static int num_sms = 0, max_clusters = 0;
     if (once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, WIDE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return (int)e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -861,7 +862,7 @@ int launch(const TcArgs& a_in, cudaStream_t st) {
     int total = a.m_tiles * a.n_tiles;
     int grid = total < num_sms ? total : num_sms;
     int units = total, workers = grid;          // work units (tiles / tile pairs) and the CTAs / clusters that walk them
-    if (a.pair) {                               // clusters of 2 CTAs, one pair of M-adjacent tiles per cluster and step
+    if (PAIR) {                                 // clusters of 2 CTAs, one pair of M-adjacent tiles per cluster and step
         static PerDeviceOnce once_c;
         if (once_c.need()) {
             // clusters of 2 that can be resident at a time (GPCs with an odd number of usable SMs leave one SM out)
@@ -874,7 +875,7 @@ int launch(const TcArgs& a_in, cudaStream_t st) {
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             int mc = 0;
-            if (cudaOccupancyMaxActiveClusters(&mc, conv_tc_kernel<BN, STAGES, WIDE>, &cfg) == cudaSuccess && mc > 0 && mc < max_clusters)
+            if (cudaOccupancyMaxActiveClusters(&mc, conv_tc_kernel<BN, STAGES, WIDE, PAIR>, &cfg) == cudaSuccess && mc > 0 && mc < max_clusters)
                 max_clusters = mc;
             (void)cudaGetLastError();
             once_c.mark();
@@ -890,8 +891,8 @@ int launch(const TcArgs& a_in, cudaStream_t st) {
         const double ideal = (double)units / workers;
         a.sk = (units > workers && (waves - ideal) / waves > 0.08) ? (int)(((long long)units * n_kb + workers - 1) / workers) : 0;
     }
-    cudaError_t e = lfdm_launch_pdl_cluster(conv_tc_kernel<BN, STAGES, WIDE>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM, st,
-                                            a.pair ? 2 : 1, a);
+    cudaError_t e = lfdm_launch_pdl_cluster(conv_tc_kernel<BN, STAGES, WIDE, PAIR>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM, st,
+                                            PAIR ? 2 : 1, a);
     if (e != cudaSuccess) return (int)e;
     return 0;
 }
@@ -1111,10 +1112,10 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
             }
         }
         switch (bn) {
-            case 128: rc = wide ? launch<128, 3, true>(a, st) : launch<128, 3, false>(a, st); break;
-            case 64: rc = wide ? launch<64, 4, true>(a, st) : launch<64, 4, false>(a, st); break;
-            case 32: rc = launch<32, 4, true>(a, st); break;
-            default: rc = launch<16, 4, true>(a, st); break;
+            case 128: rc = wide ? (a.pair ? launch<128, 3, true, true>(a, st) : launch<128, 3, true, false>(a, st)) : launch<128, 3, false, false>(a, st); break;
+            case 64: rc = wide ? (a.pair ? launch<64, 4, true, true>(a, st) : launch<64, 4, true, false>(a, st)) : launch<64, 4, false, false>(a, st); break;
+            case 32: rc = launch<32, 4, true, false>(a, st); break;
+            default: rc = launch<16, 4, true, false>(a, st); break;
         }
         if (rc) return rc;
     }
