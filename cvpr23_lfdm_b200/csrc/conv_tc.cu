@@ -45,6 +45,7 @@ struct TcArgs {
     CUtensorMap tmOut;               // fp32 [M][c_out], box {32 cols, 32 rows}, 128B swizzle (TMA-store epilogue)
     int32_t tma_store;
     int32_t dbg;                     // LFDM_CONV_DBG ablation bits (timing experiments only): 1 no A loads, 2 no B loads, 8 no TMA stores, 128 no epilogue body
+    int32_t na2;                     // 1 (default): two halo stages + six weight stages at BN = 64; LFDM_CONV_NA3=1 -> three + three
     int32_t halo, halo_plane;        // 3x3 halo mode: tmA[src*4+1] = box {64, bw, bh+2}; bytes of one halo plane
     int32_t n_taps, tap_base;
     int8_t tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
@@ -310,17 +311,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 8 * 4096);
     uint64_t* empty_bar = full_bar + MAXB;
     uint64_t* fullA_bar = empty_bar + MAXB;
-    uint64_t* emptyA_bar = fullA_bar + 2;
-    uint64_t* tfull_bar = emptyA_bar + 2;
+    uint64_t* emptyA_bar = fullA_bar + 3;
+    uint64_t* tfull_bar = emptyA_bar + 3;
     uint64_t* tempty_bar = tfull_bar + ACC;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + ACC);
     // 3x3 halo mode (see the host side): the operand ring is re-cut into 2 A stages of 48 KiB -- one (bh+2)-row halo copy
     // per horizontal tap offset dx, shared by the three vertical taps through the descriptor start address -- and a ring
     // of NB single-tap weight stages.  A bytes per tile: 3 (bh+2)/bh tiles instead of 9.
     constexpr int A_HALO_STAGE = 49152;
-    constexpr int NB = (STAGES * STAGE_BYTES - 2 * A_HALO_STAGE) / (2 * B_BYTES);
+    // ring split: NA halo stages + NB weight stages out of the same bytes: 2 + 6 (BN = 64) / 2 + 3 (BN = 128).  LFDM_CONV_NA3=1 tries
+    // 3 + 3 at BN = 64 (measured: no difference, 71.7 vs 73.6 us -- the 56 % tensor-pipe activity is not an A-ring depth problem).
+    const int NA = (BN == 64 && !a.na2) ? 3 : 2;
+    const int NB = (STAGES * STAGE_BYTES - NA * A_HALO_STAGE) / (2 * B_BYTES);
     constexpr bool HALO_OK = WIDE && BN >= 64;
-    static_assert(!HALO_OK || (NB >= 3 && NB <= MAXB), "halo-mode weight ring");
+    static_assert(!HALO_OK || ((STAGES * STAGE_BYTES - 2 * A_HALO_STAGE) / (2 * B_BYTES) <= MAXB && (STAGES * STAGE_BYTES - (BN == 64 ? 3 : 2) * A_HALO_STAGE) / (2 * B_BYTES) >= 3), "halo-mode rings");
     const bool halo = HALO_OK && a.halo;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         // pair mode: the "full" / "tmem empty" barriers of the EVEN CTA collect both CTAs (TMA bytes, epilogue threads); "empty" /
         // "tmem full" are signalled in both CTAs by the multicast commits of the even CTA's MMA thread
         for (int i = 0; i < MAXB; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&fullA_bar[i], 1); ptx::mbar_init(&emptyA_bar[i], 1); }
+        for (int i = 0; i < 3; ++i) { ptx::mbar_init(&fullA_bar[i], 1); ptx::mbar_init(&emptyA_bar[i], 1); }
         for (int i = 0; i < ACC; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], PAIR ? 256 : 128); }
         ptx::fence_barrier_init();
     }
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                     ptx::mbar_arrive_expect_tx(&fullA_bar[sa], 2 * a.halo_plane);
                                     ptx::tma_load_5d(s, tm, &fullA_bar[sa], ch * BK, w0 + dxi - 1, h0 - 1, nf0, 0);
                                     ptx::tma_load_5d(s + a.halo_plane, tm, &fullA_bar[sa], ch * BK, w0 + dxi - 1, h0 - 1, nf0, 1); }
-                                    if (++sa == 2) { sa = 0; pa ^= 1; }
+                                    if (++sa == NA) { sa = 0; pa ^= 1; }
                                 }
                             }
                     }
@@ -461,7 +465,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             for (int ch = 0; ch < a.chunks[src]; ++ch)
                                 for (int dyi = 0; dyi < 3; ++dyi) {
                                     ptx::mbar_wait(&empty_bar[sb], pb ^ 1);
-                                    uint8_t* s = smem + 2 * A_HALO_STAGE + sb * (2 * B_BYTES);
+                                    uint8_t* s = smem + NA * A_HALO_STAGE + sb * (2 * B_BYTES);
                                     if constexpr (PAIR) {
                                         if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[sb], 2 * B_BYTES);
                                         ptx::tma_load_4d_2sm(s, &a.tmBh, &full_bar[sb], kbase + ch * BK, n0 + crank * (BN / 2),
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (crank == 0 && ptx::elect_one()) {
                 constexpr uint64_t DB_STRIDE = (2 * B_BYTES) >> 4;
                 const uint64_t dA0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem));
-                const uint64_t dB0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + 2 * A_HALO_STAGE));
+                const uint64_t dB0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + NA * A_HALO_STAGE));
                 const uint64_t dy_step = (uint64_t)((a.bw * 128) >> 4), lo_step = (uint64_t)(a.halo_plane >> 4);
                 int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
                 uint64_t dA = dA0, dB = dB0;
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         }
                         if constexpr (PAIR) ptx::umma_commit_2sm(&emptyA_bar[sa], pair_mask); else ptx::umma_commit(&emptyA_bar[sa]);
                         dA += (uint64_t)(A_HALO_STAGE >> 4);
-                        if (++sa == 2) { sa = 0; pa ^= 1; dA = dA0; }
+                        if (++sa == NA) { sa = 0; pa ^= 1; dA = dA0; }
                     }
                     if constexpr (PAIR) ptx::umma_commit_2sm(&tfull_bar[as], pair_mask); else ptx::umma_commit(&tfull_bar[as]);
                 }
@@ -1004,6 +1008,10 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
     }
     // ---- 3x3 halo mode: tile inside one image, (bh+2) x bw halo copies per dx (A re-reads 9x -> 3(bh+2)/bh x)
     a.halo = 0;
+    {
+        static const bool na2 = (getenv("LFDM_CONV_NA3") == nullptr);
+        a.na2 = na2 ? 1 : 0;
+    }
     {
         static const bool allow = (getenv("LFDM_CONV_NO_HALO") == nullptr);           // A/B switch
         if (allow && d->mode == LFDM_CONV_DIRECT && d->stride == 1 && d->kh == 3 && d->kw == 3 && d->pad == 1 && bnf == 1 &&
