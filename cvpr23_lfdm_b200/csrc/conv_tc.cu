@@ -113,8 +113,8 @@ __device__ __forceinline__ void epi_chunk16(const TcArgs& a, const uint32_t (&rr
                 s0 = warp_sum(s0); q0 = warp_sum(q0); s1 = warp_sum(s1); q1 = warp_sum(q1);
                 if (lane == 0) {
                     const int g0 = nb / a.gn_cpg, g1 = (nb + 8) / a.gn_cpg;
-                    atomicAdd(gn_acc + g0 * 2, s0); atomicAdd(gn_acc + g0 * 2 + 1, q0);
-                    atomicAdd(gn_acc + g1 * 2, s1); atomicAdd(gn_acc + g1 * 2 + 1, q1);
+                    gn_acc[g0 * 2] += s0; gn_acc[g0 * 2 + 1] += q0;
+                    gn_acc[g1 * 2] += s1; gn_acc[g1 * 2 + 1] += q1;
                 }
             }
             const int64_t o = orow * a.c_out + nb;
@@ -229,8 +229,8 @@ __device__ __forceinline__ void epi_block32(const TcArgs& a, float* stage, const
         if (lanes_per_group >= 4) { gs += __shfl_xor_sync(0xffffffffu, gs, 2); gq += __shfl_xor_sync(0xffffffffu, gq, 2); }
         if (lanes_per_group >= 8) { gs += __shfl_xor_sync(0xffffffffu, gs, 4); gq += __shfl_xor_sync(0xffffffffu, gq, 4); }
         if (rsub == 0 && (cq % lanes_per_group) == 0) {
-            atomicAdd(gn_acc + (n / a.gn_cpg) * 2, gs);          // shared-memory accumulators of this epilogue group
-            atomicAdd(gn_acc + (n / a.gn_cpg) * 2 + 1, gq);
+            gn_acc[(n / a.gn_cpg) * 2] += gs;                    // this warp's own shared-memory slot: one lane per (group, k)
+            gn_acc[(n / a.gn_cpg) * 2 + 1] += gq;
         }
     }
     __syncwarp();      // stage is reused by the next block
@@ -591,17 +591,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int r = q * 32 + lane;         // tile row handled by this thread
         const bool vec_ok = (a.c_out % 16) == 0;
         float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - 4) * 1024;          // 4 KiB per warp
-        float* gn_acc = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 8 * 4096 + 256) + grp * 64;   // [group][32 x (sum, sumsq)]
+        // GroupNorm sums without float atomics (bit-reproducible): every warp owns a slot [16 groups][sum, sumsq], one lane per address
+        float* gn_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 8 * 4096 + 256);
+        float* gn_acc = gn_base + (warp - 4) * 32;
         const int tig = threadIdx.x & 127;                     // thread index inside the epilogue group
         int cur_sample = -1;
+        if (a.gn_stats) {
+            gn_acc[lane] = 0.f;
+            __syncwarp();
+        }
         auto gn_flush = [&](int next_sample) {
-            // all 4 warps of the group are between tiles here (named barrier), so the accumulators are quiescent
+            // all 4 warps of the group are between tiles here (named barrier), so the slots are quiescent.  Inside the CTA tiles
+            // and warps are added in a fixed order; ACROSS CTAs the double atomics commute exactly, because every contribution is
+            // first rounded to a multiple of 2^-24 (a no-op for |v| >= 0.5: a float has no finer bits) and sums of such multiples
+            // are exact in a double while they stay below 2^29 - the order CTAs arrive in cannot change the result.
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
             if (tig < 2 * a.gn_groups) {
-                const float v = gn_acc[tig];
+                float* s4 = gn_base + grp * 128 + tig;
+                const float v = ((s4[0] + s4[32]) + s4[64]) + s4[96];
+                s4[0] = 0.f; s4[32] = 0.f; s4[64] = 0.f; s4[96] = 0.f;
                 if (cur_sample >= 0 && v != 0.f)
-                    atomicAdd(a.gn_stats + (int64_t)cur_sample * a.gn_groups * 2 + tig, (double)v);
-                gn_acc[tig] = 0.f;
+                    atomicAdd(a.gn_stats + (int64_t)cur_sample * a.gn_groups * 2 + tig, rint((double)v * 16777216.0) * (1.0 / 16777216.0));
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
             cur_sample = next_sample;
@@ -753,7 +763,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                                 s8 = warp_sum(s8); q8 = warp_sum(q8);
                                 if (lane == 0) {
                                     const int gi = (nb + 8 * oct) / a.gn_cpg;
-                                    atomicAdd(gn_acc + gi * 2, s8); atomicAdd(gn_acc + gi * 2 + 1, q8);
+                                    gn_acc[gi * 2] += s8; gn_acc[gi * 2 + 1] += q8;
                                 }
                             }
                         }
@@ -850,7 +860,8 @@ template <int BN, int STAGES, bool WIDE, bool PAIR>
 int launch(const TcArgs& a_in, cudaStream_t st) {
     TcArgs a = a_in;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BN * BK * 2;
-    constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 8 * 4096 + 256 + 512;   // + 8 staging tiles + barriers + GN accumulators
+    constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 8 * 4096 + 256 + 1024;  // + 8 staging tiles + barriers + GN slots (8 warps x 128 B)
+    static_assert(SMEM <= 232448, "shared memory budget");
     static PerDeviceOnce once;
     static int num_sms = 0, max_clusters = 0;
     if (once.need()) {
@@ -953,7 +964,7 @@ int lfdm_conv_tc(const lfdm_conv_desc* d, cudaStream_t st) {
     else if (d->c_out <= 16) bn = 16;
     else return LFDM_E_UNSUPP;
     const int c_out_pad = ((d->c_out + bn - 1) / bn) * bn;
-    if (d->gn_stats && ((d->gn_cpg % 8) != 0 || d->rows_per_sample % 128 != 0 || mul != 1 || d->c_out / d->gn_cpg > 32)) return LFDM_E_UNSUPP;
+    if (d->gn_stats && ((d->gn_cpg % 8) != 0 || d->rows_per_sample % 128 != 0 || mul != 1 || d->c_out / d->gn_cpg > 16)) return LFDM_E_UNSUPP;
 
     TcArgs a;
     memset(&a, 0, sizeof(a));
