@@ -169,13 +169,13 @@ __device__ __forceinline__ float4 ldg_nc4(const float* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
-template <int LPP, int QPL, int U>
-__global__ void __launch_bounds__(256) warp_rows_batched_kernel(const float* __restrict__ src, const float* __restrict__ flow,
+template <int LPP, int QPL, int U, int MINB>
+__global__ void __launch_bounds__(128, MINB) warp_rows_batched_kernel(const float* __restrict__ src, const float* __restrict__ flow,
                                                                 const float* __restrict__ occ, const float* __restrict__ prev,
                                                                 float* __restrict__ out_f32, bf16* __restrict__ out_sb,
                                                                 int64_t out_plane, const float* __restrict__ sb_scale,
                                                                 const float* __restrict__ sb_shift, int sb_act, int64_t n_img,
-                                                                int frames_per_src, int hs, int ws, int hf, int wf) {
+                                                                int frames_per_src, int hs, int ws, int hf, int wf, int taps_l1, int prefetch) {
     constexpr int C = LPP * QPL * 4;
     constexpr int PPI = 32 / LPP;                            // pixels per slot row
     const int lane = threadIdx.x & 31;
@@ -192,6 +192,16 @@ __global__ void __launch_bounds__(256) warp_rows_batched_kernel(const float* __r
         sh4[qq] = sb_shift ? *reinterpret_cast<const float4*>(sb_shift + (ql + qq * LPP) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int64_t g = warp0; g < n_groups; g += nwarps) {
+        // the `prev` rows of this warp's NEXT group are the only loads that come from HBM (taps hit L1/L2): pull them into L2 now
+        if (prefetch && prev && occ && g + nwarps < n_groups) {
+            const char* nx = reinterpret_cast<const char*>(prev + ((g + nwarps) << 5) * C);
+            const int64_t lim = (total_pix - ((g + nwarps) << 5)) * C * 4;
+#pragma unroll
+            for (int l = 0; l < (32 * C * 4) / (128 * 32); ++l) {
+                const int64_t b = ((int64_t)l * 32 + lane) * 128;
+                if (b < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + b));
+            }
+        }
         // ---- phase 1: per-pixel set-up (lane = pixel)
         const int64_t pix = (g << 5) + lane;
         int off[4] = {-1, -1, -1, -1};
@@ -236,7 +246,12 @@ __global__ void __launch_bounds__(256) warp_rows_batched_kernel(const float* __r
                     const int q4 = (ql + qq * LPP) * 4;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        tap[u][qq][k] = (live[u] && o[u][k] >= 0) ? ldg_nc4(src + (int64_t)o[u][k] * C + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        // a flow field is smooth: neighbouring pixels share taps, so the source rows are worth keeping in L1
+                        // (the streamed `prev` rows are not)
+                        tap[u][qq][k] = (live[u] && o[u][k] >= 0)
+                                            ? (taps_l1 ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)o[u][k] * C + q4))
+                                                       : ldg_nc4(src + (int64_t)o[u][k] * C + q4))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
                     pv[u][qq] = (live[u] && prev && occ) ? ldg_nc4(prev + ((g << 5) + it + u * PPI + sub) * C + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
@@ -317,16 +332,37 @@ extern "C" int lfdm_warp_blend_rows(const float* src, const float* flow, const f
     int64_t blocks = (groups + 7) / 8;                  // 8 warps per block, one 32-pixel group per warp iteration
     if (blocks > 148 * 16) blocks = 148 * 16;
     if ((int64_t)n * hs * ws >= (1ll << 31) / 1 || (int64_t)(n / frames_per_src + 1) * hs * ws >= (1ll << 31)) return LFDM_E_BADARG;
+    static const int taps_l1 = (getenv("LFDM_WARP_TAPS_NO_L1") == nullptr) ? 1 : 0;      // A/B switch: taps bypass L1
     static const bool plain_env = (getenv("LFDM_WARP_PLAIN") != nullptr);       // A/B switch: one pixel slot at a time
     const bool plain = plain_env || (prev && (const void*)prev == (const void*)out_f32);   // in-place blend: no read-only path for prev
     const bool al16 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(prev) | reinterpret_cast<uintptr_t>(sb_scale) |
                         reinterpret_cast<uintptr_t>(sb_shift)) & 15) == 0;
-#define LFDM_WARP_BATCHED(LPP, QPL, U)                                                                                       \
-    warp_rows_batched_kernel<LPP, QPL, U><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(                                 \
-        src, flow, occ, prev, out_f32, (bf16*)out_sb, out_plane, sb_scale, sb_shift, sb_act, n, frames_per_src, hs, ws, hf, wf)
-    if (!plain && al16 && c == 64) LFDM_WARP_BATCHED(16, 1, 4);
-    else if (!plain && al16 && c == 128) LFDM_WARP_BATCHED(32, 1, 4);
-    else if (!plain && al16 && c == 256) LFDM_WARP_BATCHED(32, 2, 2);
+    // 128-thread blocks: at ~150 registers per thread three of them fit an SM (12 warps; a 256-thread block would sit alone with 8).
+    // The kernel is bound by instruction issue and dependent-issue waits (ncu: 90 warp instructions per pixel, 3 warps per
+    // scheduler), not by the memory system - see profiles/r02_ncu_warp_rows.md.
+    static const int prefetch = (getenv("LFDM_WARP_NO_PREFETCH") == nullptr) ? 1 : 0;
+    // slots per pass / blocks per SM: measured per channel count (profiles/r02_ncu_warp_rows.md); LFDM_WARP_VARIANT=0|1|2 forces
+    // 4 slots x 3 blocks | 4 slots x 4 blocks (128 registers) | 2 slots x 5 blocks for every channel count
+    static const int variant = getenv("LFDM_WARP_VARIANT") ? atoi(getenv("LFDM_WARP_VARIANT")) : -1;
+    int64_t bblocks = (groups + 3) / 4;
+    if (bblocks > 148 * 24) bblocks = 148 * 24;
+#define LFDM_WARP_BATCHED(LPP, QPL, U, MINB)                                                                                  \
+    warp_rows_batched_kernel<LPP, QPL, U, MINB><<<(unsigned)bblocks, 128, 0, (cudaStream_t)stream>>>(                           \
+        src, flow, occ, prev, out_f32, (bf16*)out_sb, out_plane, sb_scale, sb_shift, sb_act, n, frames_per_src, hs, ws, hf, wf, taps_l1, \
+        prefetch)
+    const bool ok = !plain && al16;
+    if (ok && c == 64 && variant == 1) LFDM_WARP_BATCHED(16, 1, 4, 4);
+    else if (ok && c == 128 && variant == 1) LFDM_WARP_BATCHED(32, 1, 4, 4);
+    else if (ok && c == 256 && variant == 1) LFDM_WARP_BATCHED(32, 2, 2, 4);
+    else if (ok && c == 64 && variant == 2) LFDM_WARP_BATCHED(16, 1, 2, 5);
+    else if (ok && c == 128 && variant == 2) LFDM_WARP_BATCHED(32, 1, 2, 5);
+    else if (ok && c == 256 && variant == 2) LFDM_WARP_BATCHED(32, 2, 1, 5);
+    else if (ok && c == 64 && variant == 0) LFDM_WARP_BATCHED(16, 1, 4, 3);
+    else if (ok && c == 128 && variant == 0) LFDM_WARP_BATCHED(32, 1, 4, 3);
+    else if (ok && c == 256 && variant == 0) LFDM_WARP_BATCHED(32, 2, 2, 3);
+    else if (ok && c == 64) LFDM_WARP_BATCHED(16, 1, 2, 5);
+    else if (ok && c == 128) LFDM_WARP_BATCHED(32, 1, 4, 4);
+    else if (ok && c == 256) LFDM_WARP_BATCHED(32, 2, 1, 5);
     else
     warp_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, flow, occ, prev, out_f32, (bf16*)out_sb,
                                                                         out_plane, sb_scale, sb_shift, sb_act, n,

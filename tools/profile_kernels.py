@@ -185,11 +185,17 @@ def cases():
         return run, 0.0, m * ch * 4 * 2, lambda: "hbm"
     c["layernorm_c64_32"] = ln
 
-    def warp(hs, ch):
+    def warp(hs, ch, smooth=False):
         def mk():
             n = B * F
             src = torch.randn(B * hs * hs, ch, device=dev)
-            flow = torch.rand(n, 32, 32, 2, device=dev) * 2 - 1
+            if smooth:
+                # what the sampler produces: the identity grid plus a displacement of a few latent pixels
+                ax = torch.linspace(-1, 1, 32, device=dev)
+                ident = torch.stack(torch.meshgrid(ax, ax, indexing="xy"), -1)
+                flow = (ident[None] + 0.15 * torch.randn(n, 1, 1, 2, device=dev) + 0.02 * torch.randn(n, 32, 32, 2, device=dev)).contiguous()
+            else:
+                flow = torch.rand(n, 32, 32, 2, device=dev) * 2 - 1            # worst case: every tap a random row of the source
             occ = torch.rand(n, 32, 32, device=dev)
             prev = torch.randn(n * hs * hs, ch, device=dev)
             out = SB(n * hs * hs, ch, dev)
@@ -200,6 +206,9 @@ def cases():
     c["warp_rows_128_c64"] = warp(128, 64)
     c["warp_rows_64_c128"] = warp(64, 128)
     c["warp_rows_32_c256"] = warp(32, 256)
+    c["warp_rows_128_c64_smooth"] = warp(128, 64, True)
+    c["warp_rows_64_c128_smooth"] = warp(64, 128, True)
+    c["warp_rows_32_c256_smooth"] = warp(32, 256, True)
 
     def wimg():
         img = torch.rand(B, 3, 128, 128, device=dev)
