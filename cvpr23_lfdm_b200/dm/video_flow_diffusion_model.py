@@ -87,6 +87,26 @@ class FlowDiffusion(nn.Module):
 
     @torch.no_grad()
     def forward(self):
+        """reference :116-143.  The reference calls region_predictor / bg_predictor / generator once per driving frame; here the
+        F frames are one batch (B*F rows, sample-major): one RegionPredictor pass, one BGMotionPredictor pass, one motion
+        hourglass pass and one decoder pass that shares the encoder output of the B source images (`Generator.forward_video`).
+        `forward_per_frame` keeps the reference's loop (same results; used by the tests as the cross-check)."""
+        b, _, nf, H, W = self.real_vid.size()
+        src = self.region_predictor(self.ref_img)
+        frames = self.real_vid.permute(0, 2, 1, 3, 4).reshape(b * nf, -1, H, W).contiguous()
+        drv = self.region_predictor(frames)
+        bg = self.bg_predictor(self.ref_img.repeat_interleave(nf, 0), frames)
+        g = self.generator.forward_video(self.ref_img, drv, src, bg, nf)
+        self.real_vid_grid = g["optical_flow"].permute(0, 4, 1, 2, 3).contiguous()          # (B, 2, F, h, w)
+        self.real_vid_conf = g["occlusion_map"].permute(0, 2, 1, 3, 4).contiguous()         # (B, 1, F, h, w)
+        self.real_out_vid, self.real_warped_vid = g["prediction"], g["deformed"]
+        self.ref_img_fea = g["bottle_neck_feat"].clone().detach()
+        if self.is_train and self.training:
+            raise NotImplementedError("diffusion training step is out of scope of the B200 inference hot path")
+
+    @torch.no_grad()
+    def forward_per_frame(self):
+        """the reference's own control flow (:116-143): one region / background / generator call per driving frame"""
         b, _, nf, H, W = self.real_vid.size()
         src = self.region_predictor(self.ref_img)
         grids, confs, outs, warps = [], [], [], []

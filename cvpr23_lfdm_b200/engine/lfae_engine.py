@@ -224,6 +224,31 @@ class GeneratorEngine:
                 "occlusion_map": occ, "prediction": pred[:, :, 0]}
 
 
+    def forward_video(self, source_image, driving_region_params, source_region_params, bg_params, f):
+        """Extension: `forward` for F driving frames per source image in ONE batch (the reference loops over the
+        frames, video_flow_diffusion_model.py:116-143).  driving_region_params / bg_params hold B*F rows (sample-major, frame-minor);
+        the encoder runs once on the B source images and the decoder shares it across the F frames of a sample."""
+        from .motion_engine import PixelwiseFlowEngine
+        if not self.has_pfp:
+            raise NotImplementedError("Generator without pixelwise_flow_predictor")
+        if self._pfp is None:
+            self._pfp = PixelwiseFlowEngine(self._gen.pixelwise_flow_predictor)
+        b = source_image.shape[0]
+        skips = self.encode(source_image)
+        rep = lambda t: t.repeat_interleave(f, 0) if torch.is_tensor(t) and t.shape[0] == b else t
+        src_rep = {k: rep(v) for k, v in source_region_params.items() if k in ("shift", "covar", "affine")}
+        mp = self._pfp.forward(rep(source_image.float()), driving_region_params, src_rep, bg_params)
+        flow = mp["optical_flow"]                                   # (B*F, h, w, 2)
+        occ = mp["occlusion_map"]                                   # (B*F, 1, h, w)
+        h, w = occ.shape[-2], occ.shape[-1]
+        pred, deformed = self.decode(source_image, skips, flow.contiguous(), occ.reshape(b * f, h, w).contiguous(), b, f)
+        rows, c, fh, fw = skips[-1]
+        fea = torch.empty((b, c, 1, fh * fw), device=self.device)
+        ops.from_rows(rows, b, c, 1, fh * fw, fea)
+        return {"bottle_neck_feat": fea.reshape(b, c, fh, fw), "deformed": deformed, "prediction": pred,
+                "optical_flow": flow.reshape(b, f, h, w, 2), "occlusion_map": occ.reshape(b, f, 1, h, w)}
+
+
 class RegionPredictorEngine:
     def __init__(self, mod):
         from .motion_engine import RegionEngine

@@ -96,33 +96,44 @@ class SamplerEngine:
         fea5 = fea.unsqueeze(2).repeat(1, 1, x.size(2), 1, 1)
         return self.gd.denoise_fn.forward_with_cond_scale(torch.cat([x, fea5], dim=1), t, cond=cond, cond_scale=cond_scale)
 
-    def _uniform_t(self, t):
-        v = t.tolist()
-        if any(a != v[0] for a in v):
-            raise NotImplementedError("per-sample different timesteps inside one p_sample call: the reference's loops "
-                                      "always pass a uniform t (video_flow_diffusion.py:756,795)")
-        return int(v[0])
+    @staticmethod
+    def _t_groups(t):
+        """{timestep: [sample indices]} - the reference indexes its schedule buffers with a per-sample t
+        (video_flow_diffusion.py:714-735 `extract(a, t, x_shape)`); its own loops pass a uniform t, which is the one-group case."""
+        groups = {}
+        for i, a in enumerate(t.tolist()):
+            groups.setdefault(int(a), []).append(i)
+        return groups
+
+    def _update_by_t(self, x, eps, noise, t, out, clip_denoised):
+        """one `_update` per distinct timestep (dynamic thresholding is per sample, so sub-batches are exact)"""
+        groups = self._t_groups(t)
+        if len(groups) == 1:
+            self._update(x, eps, noise, self._ddpm_rows(list(groups), clip_denoised), None, False, out, clip_denoised)
+            return
+        for ti, idx in groups.items():
+            ix = torch.tensor(idx, device=x.device)
+            oi = torch.empty((len(idx),) + tuple(x.shape[1:]), device=x.device)
+            self._update(x[ix].contiguous(), eps[ix].contiguous(), None if noise is None else noise[ix].contiguous(),
+                         self._ddpm_rows([ti], clip_denoised), None, False, oi, clip_denoised)
+            out[ix] = oi
 
     # ---- reference API -----------------------------------------------------------------------------------------
     def p_mean_variance(self, x, t, fea, clip_denoised, cond=None, cond_scale=1.):
         g = self.gd
-        ti = self._uniform_t(t)
         x = x.contiguous().float()
         eps = self._eps_generic(x, t, fea, cond, cond_scale).contiguous()
-        coef = self._ddpm_rows([ti], clip_denoised)
         mean = torch.empty_like(x)
-        self._update(x, eps, None, coef, None, False, mean, clip_denoised)
+        self._update_by_t(x, eps, None, t, mean, clip_denoised)
         shp = (x.shape[0],) + (1,) * (x.ndim - 1)
         return mean, g.posterior_variance[t].reshape(shp), g.posterior_log_variance_clipped[t].reshape(shp)
 
     def p_sample(self, x, t, fea, cond=None, cond_scale=1., clip_denoised=True):
-        ti = self._uniform_t(t)
         x = x.contiguous().float()
         eps = self._eps_generic(x, t, fea, cond, cond_scale).contiguous()
         noise = self.gd._randn(x.shape, x.device)
-        coef = self._ddpm_rows([ti], clip_denoised)
         out = torch.empty_like(x)
-        self._update(x, eps, noise, coef, None, False, out, clip_denoised)
+        self._update_by_t(x, eps, noise, t, out, clip_denoised)
         return out
 
     # ---- the hot loops -------------------------------------------------------------------------------------------

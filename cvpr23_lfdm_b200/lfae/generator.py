@@ -61,6 +61,12 @@ class Generator(nn.Module):
         return self.engine().decode_video(source_image, grid, conf)
 
     @torch.no_grad()
+    def forward_video(self, source_image, driving_region_params, source_region_params, bg_params, num_frames):
+        """Extension: `forward` over `num_frames` driving frames per source image in one batch (driving params / bg_params with
+        B*F rows, sample-major) -> prediction / deformed (B,3,F,H,W), optical_flow (B,F,h,w,2), occlusion_map (B,F,1,h,w)."""
+        return self.engine().forward_video(source_image, driving_region_params, source_region_params, bg_params, num_frames)
+
+    @torch.no_grad()
     def forward(self, source_image, driving_region_params, source_region_params, bg_params=None):
         """reference generator.py:90-128"""
         return self.engine().forward(source_image, driving_region_params, source_region_params, bg_params)

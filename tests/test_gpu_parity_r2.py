@@ -103,6 +103,22 @@ def test_guided_sampler_matches_reference_golden(golden, parity_log):
         out = gd.p_sample(st["x"].cuda(), t, fea, cond=cond, cond_scale=2.0)
         close(out, st["out"], f"guided p_sample t={st['t']} (teacher forced)", rtol=2e-3, atol=2e-3, log=parity_log)
 
+    # per-sample timesteps (the reference's `extract(a, t, x_shape)` indexes the schedule per sample, :714-735): sample 0 of one
+    # golden step and sample 1 of another in ONE call must reproduce the two golden outputs
+    if len(g["steps"]) >= 2 and g["steps"][0]["t"] != g["steps"][1]["t"]:
+        s0, s1 = g["steps"][0], g["steps"][1]
+        noises = []
+        for st in (s0, s1):
+            torch.manual_seed(st["seed"])
+            noises.append(torch.randn_like(st["x"]))
+        mixed_noise = torch.stack([noises[0][0], noises[1][1]])
+        gd.noise_fn = lambda shape, device, n=mixed_noise: n
+        xm = torch.stack([s0["x"][0], s1["x"][1]]).cuda()
+        tm = torch.tensor([s0["t"], s1["t"]], dtype=torch.long, device="cuda")
+        out = gd.p_sample(xm, tm, fea, cond=cond, cond_scale=2.0)
+        close(out, torch.stack([s0["out"][0], s1["out"][1]]), "guided p_sample with per-sample timesteps", rtol=2e-3, atol=2e-3,
+              log=parity_log)
+
     def chain(sampling, timesteps, seed, cs):
         d = P.GaussianDiffusion(u, image_size=8, num_frames=5, sampling_timesteps=sampling, timesteps=timesteps,
                                 loss_type='l2', use_dynamic_thres=True, null_cond_prob=0.1, ddim_sampling_eta=1.0).cuda().eval()
@@ -177,6 +193,13 @@ def test_flowdiffusion_forward_matches_reference_golden(golden, full_model, pari
     close(m.real_out_vid[..., ::8, ::8], fp["out_slice"], "FlowDiffusion.forward real_out_vid", rtol=2e-3, atol=5e-4, log=parity_log)
     close(m.real_warped_vid[..., ::8, ::8], fp["warped_slice"], "FlowDiffusion.forward real_warped_vid", rtol=2e-3, atol=5e-4, log=parity_log)
     close(m.ref_img_fea[:, ::16, ::4, ::4], fp["fea_slice"], "FlowDiffusion.forward ref_img_fea", log=parity_log)
+    # the batched branch (all driving frames in one pass) against the reference's per-frame control flow
+    batched = [t.clone() for t in (m.real_vid_grid, m.real_vid_conf, m.real_out_vid, m.real_warped_vid, m.ref_img_fea)]
+    m.forward_per_frame()
+    for name, a, r in zip(("grid", "conf", "out", "warped", "fea"), batched,
+                          (m.real_vid_grid, m.real_vid_conf, m.real_out_vid, m.real_warped_vid, m.ref_img_fea)):
+        assert a.shape == r.shape, (name, a.shape, r.shape)
+        close(a, r, f"FlowDiffusion.forward batched vs per-frame: {name}", rtol=1e-4, atol=1e-5, log=parity_log)
 
 
 def test_region_predictor_pad0_matches_reference_golden(golden, parity_log):
