@@ -29,8 +29,10 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     if (threadIdx.x == 0) {
         double a = 0, q = 0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh[0][i]; q += sh[1][i]; }
-        atomicAdd(&stats[bg * 2 + 0], a);
-        atomicAdd(&stats[bg * 2 + 1], q);
+        // contributions on a fixed 2^-24 grid: their double sums are exact, so the order the blocks arrive in cannot change the
+        // result (same scheme as the fused sums in conv_tc.cu)
+        atomicAdd(&stats[bg * 2 + 0], rint(a * 16777216.0) * (1.0 / 16777216.0));
+        atomicAdd(&stats[bg * 2 + 1], rint(q * 16777216.0) * (1.0 / 16777216.0));
     }
 }
 
