@@ -59,3 +59,14 @@ def test_no_cpu_fallback():
     u = P.Unet3D(dim=16, cond_dim=8, dim_mults=(1, 2), channels=11, attn_heads=2)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         u(torch.zeros(1, 11, 2, 8, 8), torch.zeros(1, dtype=torch.long), cond=torch.zeros(1, 8))
+
+
+def test_sampler_groups_samples_by_timestep():
+    """host logic of p_sample / p_mean_variance with a per-sample t (reference `extract(a, t, x_shape)`, video_flow_diffusion.py:592-595):
+    one update launch per distinct timestep, sample order preserved inside a group"""
+    import torch
+    from cvpr23_lfdm_b200.engine.sampler_engine import SamplerEngine
+    g = SamplerEngine._t_groups(torch.tensor([5, 0, 5, 999, 0]))
+    assert g == {5: [0, 2], 0: [1, 4], 999: [3]}
+    assert list(g) == [5, 0, 999]                       # insertion order = first occurrence
+    assert SamplerEngine._t_groups(torch.full((4,), 17)) == {17: [0, 1, 2, 3]}
